@@ -1,0 +1,341 @@
+// fluidsolver.cu -- libfluidsolver.so: CUDA executor (sm_100a) + the C ABI of include/fluidsolver.h.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false --extended-lambda
+//        -shared -Xcompiler -fPIC   (see 3dfluidsimulation_b200/build.py)
+// -fmad=false keeps the reference's unfused fp32 arithmetic (results are bit-identical to the oracle
+// for every kernel except the obstacle drag, whose exp() differs by at most 1 ulp).
+//
+// There is no CPU path in this library: every operator launches a kernel on the handle's stream.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "fs_core.h"
+#include "fs_kernels.cuh"
+
+#define FS_CUDA(call)                                                                                                  \
+    do {                                                                                                               \
+        cudaError_t e_ = (call);                                                                                       \
+        if (e_ != cudaSuccess) set_error(#call, e_);                                                                   \
+    } while (0)
+
+struct CudaExec {
+    int dev = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool bad = false;
+    std::string msg;
+    int64_t launches = 0;
+    bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
+    bool use_graph = false;
+    int sm_count = 148;
+
+    // device scratch for metrics / scatter_add
+    double *d_sum = nullptr;
+    unsigned int *d_max = nullptr;
+    void *scratch = nullptr;
+    size_t scratch_bytes = 0;
+
+    // CUDA graph cache: one executable graph per (dt, visc, diff, role configuration)
+    struct GraphEntry {
+        float dt, visc, diff;
+        float *before[11], *after[11];
+        cudaGraphExec_t exec;
+        int64_t launches;
+    };
+    std::vector<GraphEntry> graphs;
+    bool capturing = false;
+    GraphEntry pending;
+    int64_t launches_at_begin = 0;
+
+    void set_error(const char *what, cudaError_t e) {
+        if (!bad) msg = std::string(what) + ": " + cudaGetErrorString(e);
+        bad = true;
+    }
+    const std::string &error() const { return msg; }
+    bool failed() {
+        if (!bad && !capturing) {
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) set_error("kernel launch", e);
+        }
+        return bad;
+    }
+    void make_current() { cudaSetDevice(dev); }
+
+    int open(int device) {
+        dev = device;
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            msg = "no CUDA device available (libfluidsolver has no CPU path)";
+            bad = true;
+            return 1;
+        }
+        if (device < 0 || device >= count) { msg = "device_id out of range"; bad = true; return 1; }
+        FS_CUDA(cudaSetDevice(dev));
+        FS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        FS_CUDA(cudaEventCreate(&ev0));
+        FS_CUDA(cudaEventCreate(&ev1));
+        FS_CUDA(cudaMalloc(&d_sum, sizeof(double)));
+        FS_CUDA(cudaMalloc(&d_max, sizeof(unsigned int)));
+        FS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+        const char *fg = getenv("FS_FORCE_GENERIC");
+        force_generic = fg && fg[0] == '1';
+        return bad ? 1 : 0;
+    }
+    void close() {
+        invalidate_graph();
+        if (d_sum) cudaFree(d_sum);
+        if (d_max) cudaFree(d_max);
+        if (scratch) cudaFree(scratch);
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (st) cudaStreamDestroy(st);
+        d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = nullptr; st = nullptr;
+    }
+
+    // ---- memory -------------------------------------------------------------------------------
+    void *alloc(size_t bytes) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) { set_error("cudaMalloc", e); return nullptr; }
+        return p;
+    }
+    void free(void *p) { if (p) cudaFree(p); }
+    void zero(void *p, size_t bytes) { FS_CUDA(cudaMemsetAsync(p, 0, bytes, st)); }
+    void copy(void *dst, const void *src, size_t bytes) { FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, st)); }
+    void upload(void *dst, const void *src, size_t bytes) {
+        FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st));
+        FS_CUDA(cudaStreamSynchronize(st)); // the caller's buffer is only valid during the call
+    }
+    void download(void *dst, const void *src, size_t bytes) {
+        FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+    }
+    void sync() { FS_CUDA(cudaStreamSynchronize(st)); }
+    void *get_scratch(size_t bytes) {
+        if (bytes > scratch_bytes) {
+            if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
+            scratch_bytes = bytes * 2;
+            scratch = alloc(scratch_bytes);
+        }
+        return scratch;
+    }
+
+    // ---- launch helpers --------------------------------------------------------------------------
+    static void interior_planes(const FsGrid &g, int *kl0, int *count) {
+        if (!g.hz) { *kl0 = 0; *count = 1; return; }
+        const int zb = g.zoff + g.kb, ze = g.zoff + g.ke;
+        const int k0 = zb < 1 ? 1 : zb, k1 = ze > g.nz - 1 ? g.nz - 1 : ze;
+        *kl0 = k0 - g.zoff;
+        *count = k1 > k0 ? k1 - k0 : 0;
+    }
+    template <class F>
+    void cells(const FsGrid &g, F f) {
+        int kl0, cnt;
+        interior_planes(g, &kl0, &cnt);
+        if (cnt <= 0) return;
+        const dim3 block(64, 4, 1);
+        const dim3 grid((g.nx - 2 + 63) / 64, (g.ny - 2 + 3) / 4, cnt);
+        cells_kernel<<<grid, block, 0, st>>>(g, kl0, f);
+        launches++;
+    }
+    template <class F>
+    void linear(long long n, F f) {
+        if (n <= 0) return;
+        linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
+        launches++;
+    }
+
+    // ---- sweeps ----------------------------------------------------------------------------------
+    void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
+               const uint8_t *flags, float a, float c, int b, bool in_zero) {
+        int kl0, cnt;
+        interior_planes(g, &kl0, &cnt);
+        if (cnt <= 0) return;
+        if (g.nx % 4 == 0 && !force_generic) {
+            const int groups = g.nx / 4;
+            int bx = 32;
+            while (bx / 2 >= groups && bx > 1) bx /= 2;
+            const int by = 256 / bx;
+            const int gxn = (groups + bx - 1) / bx, gyn = (g.ny - 2 + by - 1) / by;
+            const long long blocks_xy = (long long)gxn * gyn;
+            const long long target = (long long)sm_count * 16; // >= 2 waves at 8 resident CTAs per SM
+            long long zchunk = (long long)cnt * blocks_xy / target;
+            if (zchunk < 16) zchunk = 16;
+            if (zchunk > 64) zchunk = 64;
+            if (zchunk > cnt) zchunk = cnt;
+            const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
+            const dim3 block(bx, by, 1), grid(gxn, gyn, nchunks);
+            const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
+            if (mode == FS_MODE_SMOOTH) {
+                if (g.hz) relax_vec4<FS_MODE_SMOOTH, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+                else relax_vec4<FS_MODE_SMOOTH, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+            } else {
+                if (g.hz) relax_vec4<FS_MODE_JACOBI, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+                else relax_vec4<FS_MODE_JACOBI, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+            }
+            launches++;
+            return;
+        }
+        if (mode == FS_MODE_SMOOTH)
+            cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+        else
+            cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+    }
+    void rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour) {
+        cells(g, [=] __device__(int i, int j, int kl) {
+            if (((i + j + kl + g.zoff) & 1) == colour) fs_rb_cell(g, x, rhs, flags, a, c, i, j, kl);
+        });
+    }
+    void bnd(const FsGrid &g, float *x, int b) {
+        cells(g, [=] __device__(int i, int j, int kl) {
+            const bool edge = i == 1 || i == g.nx - 2 || j == 1 || j == g.ny - 2 ||
+                              (g.hz && (kl + g.zoff == 1 || kl + g.zoff == g.nz - 2));
+            if (edge) fs_bnd_cell(g, x, b, i, j, kl);
+        });
+    }
+    void mirror(const FsGrid &g, float *x, const uint8_t *flags, const long long *list, long long n, int b) {
+        linear(n, [=] __device__(long long t) { fs_mirror_cell(g, x, flags, b, list[t]); });
+    }
+    void divergence(const FsGrid &g, float *div, const float *ux, const float *uy, const float *uz) {
+        cells(g, [=] __device__(int i, int j, int kl) { fs_divergence_cell(g, div, ux, uy, uz, i, j, kl); });
+    }
+    void gradient(const FsGrid &g, float *ux, float *uy, float *uz, const float *p, const uint8_t *flags) {
+        cells(g, [=] __device__(int i, int j, int kl) { fs_gradient_cell(g, ux, uy, uz, p, flags, i, j, kl); });
+    }
+    void advect(const FsGrid &g, float *d, const float *d0, const float *ux, const float *uy, const float *uz,
+                const uint8_t *flags, float dt0, int b) {
+        cells(g, [=] __device__(int i, int j, int kl) {
+            auto samp = [&](int ii, int jj, int kk) { return __ldg(d0 + fs_idx(g, ii, jj, kk - g.zoff)); };
+            fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
+        });
+    }
+    void advect_velocity(const FsGrid &g, float *dx, float *dy, float *dz, const float *sx, const float *sy,
+                         const float *sz, const uint8_t *flags, float dt0) {
+        cells(g, [=] __device__(int i, int j, int kl) {
+            auto px = [&](int ii, int jj, int kk) { return __ldg(sx + fs_idx(g, ii, jj, kk - g.zoff)); };
+            auto py = [&](int ii, int jj, int kk) { return __ldg(sy + fs_idx(g, ii, jj, kk - g.zoff)); };
+            auto pz = [&](int ii, int jj, int kk) { return __ldg(sz + fs_idx(g, ii, jj, kk - g.zoff)); };
+            fs_advect_velocity_cell(g, dx, dy, dz, px, py, pz, sx, sy, sz, flags, dt0, i, j, kl);
+        });
+    }
+    void enforce(const FsGrid &g, float *ux, float *uy, float *uz, const uint8_t *flags, float cell, float rawvisc) {
+        cells(g, [=] __device__(int i, int j, int kl) { fs_enforce_cell(g, ux, uy, uz, flags, cell, rawvisc, i, j, kl); });
+    }
+    void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
+        const long long n = g.sz * g.nzl;
+        linear(n, [=] __device__(long long t) {
+            const int i = (int)(t % g.nx), j = (int)((t / g.nx) % g.ny), kl = (int)(t / g.sz);
+            flags[t] = fs_flags_cell(g, mask, i, j, kl);
+        });
+    }
+    void axpy(float *dst, const float *src, long long n) {
+        linear(n, [=] __device__(long long t) { dst[t] += src[t]; });
+    }
+    void scatter_add(float *dst[4], const long long *idx, const float *src[4], long long n) {
+        const size_t ib = sizeof(long long) * n, fb = sizeof(float) * n;
+        char *s = (char *)get_scratch(ib + 4 * fb);
+        if (!s) return;
+        FS_CUDA(cudaMemcpyAsync(s, idx, ib, cudaMemcpyHostToDevice, st));
+        for (int f = 0; f < 4; f++)
+            if (dst[f]) FS_CUDA(cudaMemcpyAsync(s + ib + f * fb, src[f], fb, cudaMemcpyHostToDevice, st));
+        const long long *di = (const long long *)s;
+        const float *a0 = (const float *)(s + ib), *a1 = a0 + n, *a2 = a1 + n, *a3 = a2 + n;
+        float *d0 = dst[0], *d1 = dst[1], *d2 = dst[2], *d3 = dst[3];
+        // duplicates in idx are legal (two source cells clamped to one voxel): use atomics
+        linear(n, [=] __device__(long long t) {
+            const long long c = di[t];
+            if (d0) atomicAdd(d0 + c, a0[t]);
+            if (d1) atomicAdd(d1 + c, a1[t]);
+            if (d2) atomicAdd(d2 + c, a2[t]);
+            if (d3) atomicAdd(d3 + c, a3[t]);
+        });
+        FS_CUDA(cudaStreamSynchronize(st)); // host arrays are only valid during the call
+    }
+    void metrics(const FsGrid &g, const float *d, const float *ux, const float *uy, const float *uz, double *sum, float *mx) {
+        FS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), st));
+        FS_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned int), st));
+        const long long n = g.sz * (g.ke - g.kb);
+        const long long off = g.sz * g.kb;
+        double *ds = d_sum;
+        unsigned int *dm = d_max;
+        const int hz = g.hz;
+        const int blocks = sm_count * 8;
+        const long long per = (n + (long long)blocks * 256 - 1) / ((long long)blocks * 256);
+        metrics_kernel<<<blocks, 256, 0, st>>>(d + off, ux + off, uy + off, hz ? uz + off : nullptr, n, per, ds, dm);
+        launches++;
+        unsigned int bits = 0;
+        FS_CUDA(cudaMemcpyAsync(sum, d_sum, sizeof(double), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaMemcpyAsync(&bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        memcpy(mx, &bits, sizeof(float));
+    }
+
+    // ---- halo exchange (z-slabs) ---------------------------------------------------------------------
+    void halo(const FsGrid &, float *) {} // single slab: nothing to exchange (multi-GPU: DESIGN.md section 6)
+    template <class Core> int halo_export(Core &, void *) { msg = "multi-GPU halo exchange not available in this build"; return FS_ERR_UNSUPPORTED; }
+    template <class Core> int halo_connect(Core &, const void *, const void *, int) { msg = "multi-GPU halo exchange not available in this build"; return FS_ERR_UNSUPPORTED; }
+
+    // ---- CUDA graph capture / replay of one step --------------------------------------------------------
+    void invalidate_graph() {
+        for (auto &e : graphs) cudaGraphExecDestroy(e.exec);
+        graphs.clear();
+    }
+    bool replay_step(float dt, float visc, float diff, float *const before[11]) {
+        if (!use_graph) return false;
+        for (auto &e : graphs) {
+            if (e.dt == dt && e.visc == visc && e.diff == diff && memcmp(e.before, before, sizeof(e.before)) == 0) {
+                FS_CUDA(cudaGraphLaunch(e.exec, st));
+                launches += e.launches;
+                replayed = &e;
+                return true;
+            }
+        }
+        return false;
+    }
+    GraphEntry *replayed = nullptr;
+    void roles_after_replay(float **roles[11]) {
+        for (int i = 0; i < 11; i++) *roles[i] = replayed->after[i];
+    }
+    void begin_step(float dt, float visc, float diff, float *const before[11]) {
+        if (!use_graph) return;
+        pending.dt = dt; pending.visc = visc; pending.diff = diff;
+        memcpy(pending.before, before, sizeof(pending.before));
+        launches_at_begin = launches;
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) { set_error("cudaStreamBeginCapture", e); return; }
+        capturing = true;
+    }
+    void end_step(float *const after[11]) {
+        if (!capturing) return;
+        capturing = false;
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        if (e != cudaSuccess) { set_error("cudaStreamEndCapture", e); return; }
+        cudaGraphExec_t exec = nullptr;
+        e = cudaGraphInstantiate(&exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { set_error("cudaGraphInstantiate", e); return; }
+        memcpy(pending.after, after, sizeof(pending.after));
+        pending.exec = exec;
+        pending.launches = launches - launches_at_begin;
+        if (graphs.size() >= 16) invalidate_graph();
+        graphs.push_back(pending);
+        FS_CUDA(cudaGraphLaunch(exec, st)); // the captured work has not run yet
+    }
+
+    // ---- timing ------------------------------------------------------------------------------------------
+    void timer_start() { FS_CUDA(cudaEventRecord(ev0, st)); }
+    float timer_stop() {
+        float ms = 0.f;
+        FS_CUDA(cudaEventRecord(ev1, st));
+        FS_CUDA(cudaEventSynchronize(ev1));
+        FS_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+        return ms;
+    }
+};
+
+#define FS_EXEC CudaExec
+#include "fs_abi.inl"

@@ -1,0 +1,240 @@
+// fs_abi.inl -- the extern "C" surface declared in include/fluidsolver.h, implemented over
+// SolverCore<FS_EXEC>.  Included exactly once by fluidsolver.cu (FS_EXEC = CudaExec: the product) and
+// by tests/host_emul/host_emul.cpp (FS_EXEC = HostExec: CPU-only test scaffolding).
+#ifndef FS_EXEC
+#error "define FS_EXEC before including fs_abi.inl"
+#endif
+
+#include <new>
+
+struct fs_solver {
+    SolverCore<FS_EXEC> core;
+};
+
+static std::string g_create_error;
+
+#define FS_GUARD(s)                                                                                                    \
+    if (!(s)) return FS_ERR_BAD_ARGUMENT;                                                                              \
+    SolverCore<FS_EXEC> &c = (s)->core;                                                                                \
+    c.ex.make_current();
+
+extern "C" {
+
+int fs_abi_version(void) { return FS_ABI_VERSION; }
+
+int fs_create(const fs_params *params, fs_solver **out) {
+    if (!params || !out) { g_create_error = "null argument"; return FS_ERR_BAD_ARGUMENT; }
+    *out = nullptr;
+    fs_solver *s = new (std::nothrow) fs_solver();
+    if (!s) { g_create_error = "host allocation failed"; return FS_ERR_OUT_OF_MEMORY; }
+    const int rc = s->core.init(*params);
+    if (rc != FS_OK) {
+        g_create_error = s->core.err;
+        s->core.destroy();
+        delete s;
+        return rc;
+    }
+    *out = s;
+    return FS_OK;
+}
+
+void fs_destroy(fs_solver *s) {
+    if (!s) return;
+    s->core.ex.make_current();
+    s->core.destroy();
+    delete s;
+}
+
+int fs_reset(fs_solver *s) { FS_GUARD(s); return c.reset(); }
+
+const char *fs_last_error(const fs_solver *s) { return s ? s->core.err.c_str() : g_create_error.c_str(); }
+
+int fs_slab_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end, int64_t *owned_voxels) {
+    if (!s) return FS_ERR_BAD_ARGUMENT;
+    if (z_begin) *z_begin = s->core.zb;
+    if (z_end) *z_end = s->core.ze;
+    if (owned_voxels) *owned_voxels = s->core.nowned;
+    return FS_OK;
+}
+
+int fs_set_obstacles(fs_solver *s, const uint8_t *mask, int64_t n) { FS_GUARD(s); return c.set_obstacles(mask, n); }
+
+int fs_add_density(fs_solver *s, float x, float y, float z, float amount) {
+    FS_GUARD(s);
+    return c.add_cells(1, &x, &y, &z, &amount, nullptr, nullptr, nullptr);
+}
+
+int fs_add_velocity(fs_solver *s, float x, float y, float z, float ax, float ay, float az) {
+    FS_GUARD(s);
+    return c.add_cells(1, &x, &y, &z, nullptr, &ax, &ay, &az);
+}
+
+int fs_add_source_cells(fs_solver *s, int64_t count, const float *x, const float *y, const float *z,
+                        const float *density, const float *ax, const float *ay, const float *az) {
+    FS_GUARD(s);
+    return c.add_cells(count, x, y, z, density, ax, ay, az);
+}
+
+int fs_add_sources(fs_solver *s, const float *density, const float *vx, const float *vy, const float *vz) {
+    FS_GUARD(s);
+    return c.add_dense(density, vx, vy, vz);
+}
+
+int fs_step(fs_solver *s, float dt, float visc, float diff) { FS_GUARD(s); return c.step(dt, visc, diff); }
+
+int fs_sync(fs_solver *s) { FS_GUARD(s); c.ex.sync(); return c.check(); }
+
+int fs_get_field(fs_solver *s, int32_t field, float *out, int64_t n) { FS_GUARD(s); return c.get_field(field, out, n); }
+
+int fs_set_field(fs_solver *s, int32_t field, const float *in, int64_t n) { FS_GUARD(s); return c.set_field(field, in, n); }
+
+int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density) {
+    FS_GUARD(s);
+    double sum = 0.0;
+    float mx = 0.0f;
+    c.ex.metrics(c.g, c.density, c.vx, c.vy, c.vz, &sum, &mx);
+    if (sum_density) *sum_density = sum;
+    if (mean_density) *mean_density = (float)(sum / (double)c.nowned);
+    if (max_speed) *max_speed = mx;
+    return c.check();
+}
+
+// ---- operator entry points ---------------------------------------------------------------------------
+static bool fs_valid_b(const SolverCore<FS_EXEC> &c, int b) { return b >= 0 && b <= (c.g.hz ? 3 : 2); }
+
+int fs_op_set_bnd(fs_solver *s, int32_t field, int32_t b) {
+    FS_GUARD(s);
+    float *p = c.field_ptr(field);
+    if (!p || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad field or b");
+    c.ex.bnd(c.g, p, b);
+    c.mirror(p, b);
+    c.ex.halo(c.g, p);
+    return c.check();
+}
+
+int fs_op_smooth(fs_solver *s, int32_t dst, int32_t src, int32_t b, float a, float cc, int32_t iters) {
+    FS_GUARD(s);
+    float **d = c.field_slot(dst);
+    float *x0 = c.field_ptr(src);
+    if (!d || !*d || !x0 || dst == src || !fs_valid_b(c, b) || iters < 0) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    c.smooth(b, *d, x0, a, cc, iters);
+    return c.check();
+}
+
+int fs_op_lin_solve(fs_solver *s, int32_t dst, int32_t rhs, int32_t b, float a, float cc, int32_t iters,
+                    int32_t solver_kind) {
+    FS_GUARD(s);
+    float **d = c.field_slot(dst);
+    float *r = c.field_ptr(rhs);
+    if (!d || !*d || !r || dst == rhs || !fs_valid_b(c, b) || iters < 0) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    if (solver_kind == FS_RED_BLACK)
+        c.lin_solve_rb(b, *d, r, a, cc, iters, false);
+    else
+        c.lin_solve(b, *d, r, a, cc, iters, false);
+    return c.check();
+}
+
+int fs_op_diffuse(fs_solver *s, int32_t dst, int32_t src, int32_t b, float diff, float dt) {
+    FS_GUARD(s);
+    float **d = c.field_slot(dst);
+    float *x0 = c.field_ptr(src);
+    if (!d || !*d || !x0 || dst == src || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    c.diffuse(b, *d, x0, diff, dt);
+    return c.check();
+}
+
+int fs_op_project(fs_solver *s, int32_t use_v0_fields) {
+    FS_GUARD(s);
+    if (use_v0_fields) c.project(c.vx0, c.vy0, c.vz0);
+    else c.project(c.vx, c.vy, c.vz);
+    return c.check();
+}
+
+int fs_op_advect(fs_solver *s, int32_t dst, int32_t src, int32_t b, int32_t use_v0_fields, float dt) {
+    FS_GUARD(s);
+    float *d = c.field_ptr(dst), *d0 = c.field_ptr(src);
+    if (!d || !d0 || dst == src || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    float *ux = use_v0_fields ? c.vx0 : c.vx, *uy = use_v0_fields ? c.vy0 : c.vy, *uz = use_v0_fields ? c.vz0 : c.vz;
+    if (d == ux || d == uy || d == uz) return c.fail(FS_ERR_BAD_ARGUMENT, "dst aliases the carrier velocity");
+    const float dt0 = dt * (float)(c.g.nx - 2);
+    c.ex.advect(c.g, d, d0, ux, uy, uz, c.fl(), dt0, b);
+    c.mirror(d, b);
+    c.ex.halo(c.g, d);
+    return c.check();
+}
+
+int fs_op_advect_velocity(fs_solver *s, float dt) {
+    FS_GUARD(s);
+    const float dt0 = dt * (float)(c.g.nx - 2);
+    c.ex.advect_velocity(c.g, c.vx, c.vy, c.vz, c.vx0, c.vy0, c.vz0, c.fl(), dt0);
+    c.mirror(c.vx, 1);
+    c.mirror(c.vy, 2);
+    if (c.g.hz) c.mirror(c.vz, 3);
+    c.ex.halo(c.g, c.vx);
+    c.ex.halo(c.g, c.vy);
+    if (c.g.hz) c.ex.halo(c.g, c.vz);
+    return c.check();
+}
+
+int fs_op_enforce_obstacles(fs_solver *s) {
+    FS_GUARD(s);
+    if (c.any_obstacle) {
+        c.ex.enforce(c.g, c.vx, c.vy, c.vz, c.flags, c.prm.cell_size, c.prm.raw_viscosity);
+        c.ex.halo(c.g, c.vx);
+        c.ex.halo(c.g, c.vy);
+        if (c.g.hz) c.ex.halo(c.g, c.vz);
+    }
+    return c.check();
+}
+
+// ---- measurement ---------------------------------------------------------------------------------------
+int fs_timer_start(fs_solver *s) { FS_GUARD(s); c.ex.timer_start(); return c.check(); }
+
+int fs_timer_stop(fs_solver *s, float *elapsed_ms) {
+    FS_GUARD(s);
+    const float ms = c.ex.timer_stop();
+    if (elapsed_ms) *elapsed_ms = ms;
+    return c.check();
+}
+
+int64_t fs_launch_count(const fs_solver *s) { return s ? s->core.ex.launches : 0; }
+
+int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes) {
+    FS_GUARD(s);
+    if (reps < 1 || kind < 0 || kind > 2 || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    // scratch operands: in = vx0, rhs = vy0, out = tmp (contents are whatever the last step left there)
+    const long long interior = (long long)(c.g.nx) * c.g.ny * (c.ze - c.zb);
+    const double per_voxel = kind == 0 ? 9.0 : 13.0;
+    float a, cc;
+    SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
+    for (int w = 0; w < 2; w++) { // warm-up
+        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
+        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false);
+    }
+    c.ex.timer_start();
+    for (int r = 0; r < reps; r++) {
+        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
+        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false);
+    }
+    const float ms = c.ex.timer_stop();
+    if (avg_ms) *avg_ms = ms / (float)reps;
+    if (algo_bytes) *algo_bytes = per_voxel * (double)interior;
+    return c.check();
+}
+
+// ---- multi-GPU wiring ------------------------------------------------------------------------------------
+int fs_halo_export(fs_solver *s, void *blob, int64_t blob_bytes) {
+    FS_GUARD(s);
+    if (!blob || blob_bytes < FS_IPC_BLOB_BYTES) return c.fail(FS_ERR_BAD_ARGUMENT, "blob too small");
+    memset(blob, 0, (size_t)blob_bytes);
+    const int rc = c.ex.halo_export(c, blob);
+    return rc ? c.fail(rc, c.ex.error()) : FS_OK;
+}
+
+int fs_halo_connect(fs_solver *s, const void *lower_blob, const void *upper_blob, int32_t same_process) {
+    FS_GUARD(s);
+    const int rc = c.ex.halo_connect(c, lower_blob, upper_blob, same_process);
+    return rc ? c.fail(rc, c.ex.error()) : FS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,347 @@
+// fs_cellops.cuh -- per-cell arithmetic of the stable-fluids step, shared by every kernel.
+//
+// Each function is the body of one reference Burst job (Assets/Scripts/FluidSim.cs) generalised to
+// 3D as specified in DESIGN.md section 2, evaluated for ONE interior cell, plus the set_bnd
+// (BoundaryJob, :1235-1289) ring cells that derive from that cell ("ring scatter"): the thread
+// that owns interior cell (1,j,k) also writes face cell (0,j,k), and so on for edges and corners.
+// fp32, reference association order, z terms appended last, true division.  Compiled with
+// -fmad=false so that nvcc does not contract a*s + r into an FMA (Burst's strict float mode).
+//
+// The functions are __host__ __device__ and free of CUDA-only constructs so that the CPU test
+// suite can compile them with g++ (tests/host_emul) and check the ring/obstacle logic against the
+// oracle without a GPU.  The product only ever runs them on the device.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define FS_HD __host__ __device__ __forceinline__
+#else
+#define FS_HD inline
+#endif
+
+// Obstacle flag byte, built once per fs_set_obstacles (kernel build_flags):
+//   bit0 self is obstacle; bit1/2 x-1/x+1 neighbour is obstacle; bit3/4 y-1/y+1; bit5/6 z-1/z+1.
+// Out-of-grid neighbours count as fluid (they are never consulted for interior cells).
+enum : uint8_t {
+    FS_OB_SELF = 1, FS_OB_XM = 2, FS_OB_XP = 4, FS_OB_YM = 8, FS_OB_YP = 16, FS_OB_ZM = 32, FS_OB_ZP = 64
+};
+
+enum { FS_MODE_SMOOTH = 0, FS_MODE_JACOBI = 1 };
+
+// Geometry of one z-slab.  Local arrays hold planes [zoff, zoff+nzl) of the global grid; the slab
+// owns local planes [kb, ke) and the rest are ghosts filled by the halo exchange.
+struct FsGrid {
+    int nx, ny, nz;   // GLOBAL dimensions; N ("size") = nx
+    int hz;           // nz > 1
+    int zoff;         // global z of local plane 0
+    int nzl;          // local planes allocated
+    int kb, ke;       // owned local planes [kb, ke)
+    long long sy, sz; // strides nx, nx*ny
+};
+
+FS_HD long long fs_idx(const FsGrid &g, int i, int j, int kl) { return i + j * g.sy + kl * g.sz; }
+
+// Value of a set_bnd ring cell whose nearest interior cell holds v (pre-obstacle-mirroring value).
+// fx/fy/fz: the ring cell lies on an x/y/z boundary plane.  b: field kind (1/2/3 negate across
+// that axis).  Faces :1246-1252, 2D corners :1255-1258; 3D edges = 0.5*(two adjacent face cells),
+// 3D corners = (three adjacent edge cells)/3, in x,y,z order.
+FS_HD float fs_ring_value(float v, int fx, int fy, int fz, int b) {
+    const float sx = b == 1 ? -v : v, sy = b == 2 ? -v : v, sz = b == 3 ? -v : v;
+    const int n = fx + fy + fz;
+    if (n == 0) return v;
+    if (n == 1) return fx ? sx : (fy ? sy : sz);
+    if (n == 2) {
+        if (fx && fy) return 0.5f * (sy + sx); // (1,0,k) is a y-face cell, (0,1,k) an x-face cell
+        if (fx && fz) return 0.5f * (sz + sx);
+        return 0.5f * (sz + sy);
+    }
+    const float ex = 0.5f * (sz + sy), ey = 0.5f * (sz + sx), ez = 0.5f * (sy + sx);
+    return ((ex + ey) + ez) / 3.0f;
+}
+
+// Calls emit(ii, jj, kl, fx, fy, fz) for interior cell (i,j,kl) itself (flags 0) and for every ring
+// cell whose nearest interior cell it is.  k is the GLOBAL z of local plane kl.
+template <class Emit>
+FS_HD void fs_ring_scatter(const FsGrid &g, int i, int j, int kl, Emit emit) {
+    const int k = kl + g.zoff;
+    int xs[3], ys[3], zs[3], fxs[3], fys[3], fzs[3];
+    int nxs = 0, nys = 0, nzs = 0;
+    xs[nxs] = i; fxs[nxs++] = 0;
+    if (i == 1) { xs[nxs] = 0; fxs[nxs++] = 1; }
+    if (i == g.nx - 2) { xs[nxs] = g.nx - 1; fxs[nxs++] = 1; }
+    ys[nys] = j; fys[nys++] = 0;
+    if (j == 1) { ys[nys] = 0; fys[nys++] = 1; }
+    if (j == g.ny - 2) { ys[nys] = g.ny - 1; fys[nys++] = 1; }
+    zs[nzs] = kl; fzs[nzs++] = 0;
+    if (g.hz) {
+        if (k == 1) { zs[nzs] = kl - 1; fzs[nzs++] = 1; }
+        if (k == g.nz - 2) { zs[nzs] = kl + 1; fzs[nzs++] = 1; }
+    }
+    for (int c = 0; c < nzs; c++)
+        for (int bq = 0; bq < nys; bq++)
+            for (int a = 0; a < nxs; a++) emit(xs[a], ys[bq], zs[c], fxs[a], fys[bq], fzs[c]);
+}
+
+// ---- relaxation sweeps ---------------------------------------------------------------------------
+// MODE SMOOTH: DiffuseJob :1045-1068  out = (in[c] + a*nbsum(in))/c, obstacle cells keep the stale
+//              content of the output buffer (`stale`: x0 during the first two iterations because both
+//              reference buffers start as copies of x0 (:1299-1300); afterwards the buffer itself,
+//              signalled by stale == nullptr).
+// MODE JACOBI: LinearSolveIterationJob :1200-1231  out = (rhs[c] + a*nbsum(in))/c, obstacle: copy.
+// in_zero: the read buffer is identically zero (first pressure iteration, :1094/:1427) and is not loaded.
+template <int MODE>
+FS_HD void fs_relax_cell(const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
+                         const uint8_t *flags, float a, float c, int b, bool in_zero, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    const bool obst = flags && (flags[idx] & FS_OB_SELF);
+    float v;
+    bool write_self = true;
+    if (obst) {
+        if (MODE == FS_MODE_JACOBI) {
+            v = in_zero ? 0.0f : in[idx];
+        } else if (stale) {
+            v = stale[idx];
+        } else {
+            v = out[idx];
+            write_self = false;
+        }
+    } else {
+        float s;
+        if (in_zero) {
+            s = ((0.0f + 0.0f) + 0.0f) + 0.0f;
+            if (g.hz) s = (s + 0.0f) + 0.0f;
+        } else {
+            s = ((in[idx + 1] + in[idx - 1]) + in[idx + g.sy]) + in[idx - g.sy];
+            if (g.hz) s = (s + in[idx + g.sz]) + in[idx - g.sz];
+        }
+        const float r = MODE == FS_MODE_JACOBI ? rhs[idx] : in[idx];
+        v = (r + a * s) / c;
+    }
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        if (fx | fy | fz) out[fs_idx(g, ii, jj, kk)] = fs_ring_value(v, fx, fy, fz, b);
+        else if (write_self) out[idx] = v;
+    });
+}
+
+// Red-black half sweep (colour = (i+j+k)&1 with GLOBAL k), in place, no ring writes; set_bnd is a
+// separate pass after both colours (oracle fo_lin_solve_rb).
+FS_HD void fs_rb_cell(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c,
+                      int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    if (flags && (flags[idx] & FS_OB_SELF)) return;
+    float s = ((x[idx + 1] + x[idx - 1]) + x[idx + g.sy]) + x[idx - g.sy];
+    if (g.hz) s = (s + x[idx + g.sz]) + x[idx - g.sz];
+    x[idx] = (rhs[idx] + a * s) / c;
+}
+
+// set_bnd faces/edges/corners only, from the interior values already in x (used after red-black and
+// by fs_op_set_bnd).  Interior cell is left untouched.
+FS_HD void fs_bnd_cell(const FsGrid &g, float *x, int b, int i, int j, int kl) {
+    const float v = x[fs_idx(g, i, j, kl)];
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        if (fx | fy | fz) x[fs_idx(g, ii, jj, kk)] = fs_ring_value(v, fx, fy, fz, b);
+    });
+}
+
+// Obstacle mirroring of BoundaryJob :1261-1287 for one interior obstacle cell (b = 1, 2 or 3).
+// Runs after the sweep that produced x (it reads the NEW values of fluid neighbours and ring cells).
+FS_HD void fs_mirror_cell(const FsGrid &g, float *x, const uint8_t *flags, int b, long long idx) {
+    const long long step = b == 1 ? 1 : (b == 2 ? g.sy : g.sz);
+    const uint8_t f = flags[idx];
+    const uint8_t lo = b == 1 ? FS_OB_XM : (b == 2 ? FS_OB_YM : FS_OB_ZM);
+    const uint8_t hi = b == 1 ? FS_OB_XP : (b == 2 ? FS_OB_YP : FS_OB_ZP);
+    float m = 0.0f;
+    int count = 0;
+    if (!(f & lo)) { m += -x[idx - step]; count++; }
+    if (!(f & hi)) { m += -x[idx + step]; count++; }
+    x[idx] = count > 0 ? m / (float)count : 0.0f;
+}
+
+// ---- projection -----------------------------------------------------------------------------------
+// ProjectDivergenceJob :1080-1095 (obstacle cells included) + BoundaryJob(b=0) on div.  p is not
+// written: the first pressure iteration runs with in_zero instead (:1094, :1427).
+FS_HD void fs_divergence_cell(const FsGrid &g, float *div, const float *vx, const float *vy, const float *vz,
+                              int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    float s = ((vx[idx + 1] - vx[idx - 1]) + vy[idx + g.sy]) - vy[idx - g.sy];
+    if (g.hz) s = (s + vz[idx + g.sz]) - vz[idx - g.sz];
+    const float v = -0.5f * s / (float)g.nx;
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        div[fs_idx(g, ii, jj, kk)] = fs_ring_value(v, fx, fy, fz, 0);
+    });
+}
+
+// ProjectVelocityAdjustJob :1107-1122 + BoundaryJob(b=1/2/3) faces; in place.  Only the owning
+// thread touches a velocity cell and its ring cells, so in-place is race free.
+FS_HD void fs_gradient_cell(const FsGrid &g, float *vx, float *vy, float *vz, const float *p,
+                            const uint8_t *flags, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    const bool obst = flags && (flags[idx] & FS_OB_SELF);
+    float nvx = vx[idx], nvy = vy[idx], nvz = g.hz ? vz[idx] : 0.0f;
+    if (!obst) {
+        nvx = nvx - 0.5f * (p[idx + 1] - p[idx - 1]) * (float)g.nx;
+        nvy = nvy - 0.5f * (p[idx + g.sy] - p[idx - g.sy]) * (float)g.nx;
+        if (g.hz) nvz = nvz - 0.5f * (p[idx + g.sz] - p[idx - g.sz]) * (float)g.nx;
+    }
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        const long long o = fs_idx(g, ii, jj, kk);
+        if (fx | fy | fz) {
+            vx[o] = fs_ring_value(nvx, fx, fy, fz, 1);
+            vy[o] = fs_ring_value(nvy, fx, fy, fz, 2);
+            if (g.hz) vz[o] = fs_ring_value(nvz, fx, fy, fz, 3);
+        } else if (!obst) {
+            vx[o] = nvx;
+            vy[o] = nvy;
+            if (g.hz) vz[o] = nvz;
+        }
+    });
+}
+
+// ---- advection -------------------------------------------------------------------------------------
+// AdvectJob :1138-1185: back-trace, clamp, bi/trilinear weights.  `samp(ii,jj,kk)` fetches the
+// advected field at GLOBAL integer coordinates (it resolves slab ownership).
+struct FsAdvectWeights {
+    int i0, j0, k0;
+    float s0, s1, t0, t1, u0, u1;
+};
+
+FS_HD FsAdvectWeights fs_advect_weights(const FsGrid &g, float dt0, float velx, float vely, float velz, int i, int j,
+                                        int k) {
+    FsAdvectWeights w;
+    float x = (float)i - dt0 * velx;
+    float y = (float)j - dt0 * vely;
+    if (x < 0.5f) x = 0.5f;
+    if (x > (float)g.nx - 1.5f) x = (float)g.nx - 1.5f;
+    w.i0 = (int)x;
+    if (y < 0.5f) y = 0.5f;
+    if (y > (float)g.ny - 1.5f) y = (float)g.ny - 1.5f;
+    w.j0 = (int)y;
+    w.s1 = x - (float)w.i0;
+    w.s0 = 1.0f - w.s1;
+    w.t1 = y - (float)w.j0;
+    w.t0 = 1.0f - w.t1;
+    w.k0 = 0;
+    w.u0 = 1.0f;
+    w.u1 = 0.0f;
+    if (g.hz) {
+        float z = (float)k - dt0 * velz;
+        if (z < 0.5f) z = 0.5f;
+        if (z > (float)g.nz - 1.5f) z = (float)g.nz - 1.5f;
+        w.k0 = (int)z;
+        w.u1 = z - (float)w.k0;
+        w.u0 = 1.0f - w.u1;
+    }
+    return w;
+}
+
+template <class Samp>
+FS_HD float fs_advect_interp(const FsGrid &g, const FsAdvectWeights &w, Samp samp) {
+    const int i0 = w.i0, i1 = w.i0 + 1, j0 = w.j0, j1 = w.j0 + 1;
+    const float lo = w.s0 * (w.t0 * samp(i0, j0, w.k0) + w.t1 * samp(i0, j1, w.k0)) +
+                     w.s1 * (w.t0 * samp(i1, j0, w.k0) + w.t1 * samp(i1, j1, w.k0)); // :1183-1184
+    if (!g.hz) return lo;
+    const int k1 = w.k0 + 1;
+    const float hi = w.s0 * (w.t0 * samp(i0, j0, k1) + w.t1 * samp(i0, j1, k1)) +
+                     w.s1 * (w.t0 * samp(i1, j0, k1) + w.t1 * samp(i1, j1, k1));
+    return w.u0 * lo + w.u1 * hi;
+}
+
+// One scalar field (b = 0 density, or a single velocity component): obstacle cells get 0 because the
+// reference's output array is freshly cleared (:1529, :1148-1156); ring via set_bnd(b).
+template <class Samp>
+FS_HD void fs_advect_cell(const FsGrid &g, float *d, Samp samp, const float *velx, const float *vely,
+                          const float *velz, const uint8_t *flags, float dt0, int b, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    float v = 0.0f;
+    if (!(flags && (flags[idx] & FS_OB_SELF))) {
+        const FsAdvectWeights w =
+            fs_advect_weights(g, dt0, velx[idx], vely[idx], g.hz ? velz[idx] : 0.0f, i, j, kl + g.zoff);
+        v = fs_advect_interp(g, w, samp);
+    }
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        d[fs_idx(g, ii, jj, kk)] = fs_ring_value(v, fx, fy, fz, b);
+    });
+}
+
+// Self-advection of the velocity (VelocityStep :710-711): all components share one back-trace
+// because every AdvectWithJobs call there uses the same (velocityX0, velocityY0) as carrier.
+template <class SampX, class SampY, class SampZ>
+FS_HD void fs_advect_velocity_cell(const FsGrid &g, float *dx, float *dy, float *dz, SampX sampx, SampY sampy,
+                                   SampZ sampz, const float *velx, const float *vely, const float *velz,
+                                   const uint8_t *flags, float dt0, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    float ax = 0.0f, ay = 0.0f, az = 0.0f;
+    if (!(flags && (flags[idx] & FS_OB_SELF))) {
+        const FsAdvectWeights w =
+            fs_advect_weights(g, dt0, velx[idx], vely[idx], g.hz ? velz[idx] : 0.0f, i, j, kl + g.zoff);
+        ax = fs_advect_interp(g, w, sampx);
+        ay = fs_advect_interp(g, w, sampy);
+        if (g.hz) az = fs_advect_interp(g, w, sampz);
+    }
+    fs_ring_scatter(g, i, j, kl, [&](int ii, int jj, int kk, int fx, int fy, int fz) {
+        const long long o = fs_idx(g, ii, jj, kk);
+        dx[o] = fs_ring_value(ax, fx, fy, fz, 1);
+        dy[o] = fs_ring_value(ay, fx, fy, fz, 2);
+        if (g.hz) dz[o] = fs_ring_value(az, fx, fy, fz, 3);
+    });
+}
+
+// ---- obstacle post-pass ---------------------------------------------------------------------------
+// EnforceObstacleBoundaries + ApplyDragNearObstacle :617-673, per cell: obstacle -> V = 0; fluid cell
+// -> V *= f(|V|) once per INTERIOR obstacle neighbour, |V| recomputed each time.
+FS_HD float fs_drag_factor(float U, float cell, float rawvisc) {
+    const float visc = rawvisc > 1e-5f ? rawvisc : 1e-5f;
+    const float Re = (U * cell) / visc;
+    float t = 1.0f - (float)exp((double)(-Re * 0.01f)); // Mathf.Exp is (float)Math.Exp((double)x)
+    if (t < 0.0f) t = 0.0f;
+    if (t > 1.0f) t = 1.0f;
+    return 0.8f + (0.98f - 0.8f) * t;
+}
+
+FS_HD void fs_enforce_cell(const FsGrid &g, float *vx, float *vy, float *vz, const uint8_t *flags, float cell,
+                           float rawvisc, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    const uint8_t f = flags[idx];
+    if (f == 0) return;
+    if (f & FS_OB_SELF) {
+        vx[idx] = 0.0f;
+        vy[idx] = 0.0f;
+        if (g.hz) vz[idx] = 0.0f;
+        return;
+    }
+    const int k = kl + g.zoff;
+    int n = 0;
+    if ((f & FS_OB_XM) && i - 1 >= 1) n++;
+    if ((f & FS_OB_XP) && i + 1 <= g.nx - 2) n++;
+    if ((f & FS_OB_YM) && j - 1 >= 1) n++;
+    if ((f & FS_OB_YP) && j + 1 <= g.ny - 2) n++;
+    if (g.hz && (f & FS_OB_ZM) && k - 1 >= 1) n++;
+    if (g.hz && (f & FS_OB_ZP) && k + 1 <= g.nz - 2) n++;
+    if (n == 0) return;
+    float ax = vx[idx], ay = vy[idx], az = g.hz ? vz[idx] : 0.0f;
+    for (int r = 0; r < n; r++) {
+        float q = ax * ax + ay * ay;
+        if (g.hz) q = q + az * az;
+        const float U = sqrtf(q); // == (float)sqrt((double)q): sqrt is correctly rounded in both
+        const float fac = fs_drag_factor(U, cell, rawvisc);
+        ax *= fac;
+        ay *= fac;
+        az *= fac;
+    }
+    vx[idx] = ax;
+    vy[idx] = ay;
+    if (g.hz) vz[idx] = az;
+}
+
+// Flag byte of one cell from the raw 0/1 mask (local array incl. ghost planes).
+FS_HD uint8_t fs_flags_cell(const FsGrid &g, const uint8_t *mask, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    uint8_t f = mask[idx] ? FS_OB_SELF : 0;
+    if (i > 0 && mask[idx - 1]) f |= FS_OB_XM;
+    if (i < g.nx - 1 && mask[idx + 1]) f |= FS_OB_XP;
+    if (j > 0 && mask[idx - g.sy]) f |= FS_OB_YM;
+    if (j < g.ny - 1 && mask[idx + g.sy]) f |= FS_OB_YP;
+    if (kl > 0 && mask[idx - g.sz]) f |= FS_OB_ZM;
+    if (kl < g.nzl - 1 && mask[idx + g.sz]) f |= FS_OB_ZP;
+    return f;
+}

@@ -1,0 +1,168 @@
+// fs_kernels.cuh -- sm_100a kernels of the stable-fluids step.
+//
+// Two families:
+//  * relax_vec4: the hot sweep (pass-1 smoother / Jacobi; 320 of the 328 sweeps of a 512^3 K_p=80
+//    step).  One thread owns a float4 of x for one row and marches in z, keeping the z-1/z/z+1
+//    centre values in registers; y and x neighbours come through L1 (read-only path), rhs/flags are
+//    streamed with L1::no_allocate.  set_bnd faces/edges/corners are written by the owning thread as
+//    whole float4 rows ("ring scatter"), so no separate boundary pass exists.  HBM-bound: 13 B/voxel
+//    (Jacobi) or 9 B/voxel (smoother); no tensor cores (no contraction anywhere on this path).
+//  * cells_kernel<F>: one thread per interior cell running a fs_cellops.cuh functor.  Used for the
+//    once-per-step kernels (divergence, gradient, advect, obstacle pass) and as the scalar fallback
+//    of the sweeps when nx % 4 != 0.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "fs_cellops.cuh"
+
+// ---- generic per-cell launch ------------------------------------------------------------------------
+template <class F>
+__global__ void __launch_bounds__(256) cells_kernel(FsGrid g, int kl0, F f) {
+    const int i = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = kl0 + blockIdx.z;
+    if (i <= g.nx - 2 && j <= g.ny - 2) f(i, j, kl);
+}
+
+template <class F>
+__global__ void __launch_bounds__(256) linear_kernel(long long n, F f) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) f(t);
+}
+
+// ---- vector loads/stores ---------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float4 ld4_stream(const float *p) { // read once: do not allocate in L1
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float4 ld4_plain(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ uint32_t ld_flags4(const uint8_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st4(float *p, const float v[4]) {
+    *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// ---- the hot sweep ---------------------------------------------------------------------------------
+// Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
+// Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
+// kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
+template <int MODE, bool HZ>
+__global__ void __launch_bounds__(256)
+relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
+           float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
+           const int in_zero, const int kl_begin, const int kl_end, const int zchunk) {
+    const int gx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x0 = gx * 4;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    if (x0 >= g.nx || j > g.ny - 2) return;
+    const int k_lo = kl_begin + blockIdx.z * zchunk;
+    const int k_hi = min(k_lo + zchunk, kl_end);
+    if (k_lo >= k_hi) return;
+
+    const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
+    const int fxl[4] = {first_x ? 1 : 0, 0, 0, last_x ? 1 : 0};
+    const float *stale_src = stale ? stale : out;
+
+    long long idx = fs_idx(g, x0, j, k_lo);
+    float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
+    if (!in_zero) {
+        cur = ld4(in + idx);
+        if (HZ) prev = ld4(in + idx - g.sz);
+    }
+
+    for (int kl = k_lo; kl < k_hi; kl++, idx += g.sz) {
+        float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
+        float left = 0.f, right = 0.f;
+        if (!in_zero) {
+            if (HZ) next = ld4(in + idx + g.sz);
+            up = ld4(in + idx + g.sy);
+            dn = ld4(in + idx - g.sy);
+            if (!first_x) left = __ldg(in + idx - 1);
+            if (!last_x) right = __ldg(in + idx + 4);
+        }
+        float4 r4 = cur;
+        if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(rhs + idx);
+        const uint32_t fl = flags ? ld_flags4(flags + idx) : 0u;
+
+        const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
+        const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+        const float nxv[4] = {next.x, next.y, next.z, next.w}, pvv[4] = {prev.x, prev.y, prev.z, prev.w};
+        const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+        float st[4] = {0.f, 0.f, 0.f, 0.f};
+        if (MODE == FS_MODE_SMOOTH && (fl & 0x01010101u)) {
+            const float4 s4 = ld4_plain(stale_src + idx);
+            st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
+        }
+        float v[4];
+#pragma unroll
+        for (int l = 0; l < 4; l++) {
+            const bool obst = (fl >> (8 * l)) & 1u;
+            float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
+            if (HZ) s = (s + nxv[l]) + pvv[l];
+            const float val = (rv[l] + a * s) / c;
+            v[l] = obst ? (MODE == FS_MODE_JACOBI ? cv[l + 1] : st[l]) : val;
+        }
+        // ring lanes take their nearest interior lane's value; fs_ring_value applies the x-face rule
+        if (first_x) v[0] = v[1];
+        if (last_x) v[3] = v[2];
+
+        const int k = kl + g.zoff;
+        const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);       // extra ring row (y)
+        const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;          // ny == 3: both
+        const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
+        const int kr2 = (HZ && k == 1 && k == g.nz - 2) ? kl + 1 : -1;      // nz == 3: both
+        const int zs[3] = {kl, kr, kr2}, fzs[3] = {0, 1, 1};
+        const int ys[3] = {j, jr, jr2}, fys[3] = {0, 1, 1};
+#pragma unroll
+        for (int zi = 0; zi < 3; zi++) {
+            if (zi > 0 && zs[zi] < 0) continue;
+#pragma unroll
+            for (int yi = 0; yi < 3; yi++) {
+                if (yi > 0 && ys[yi] < 0) continue;
+                float o[4];
+#pragma unroll
+                for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
+                st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+            }
+        }
+        prev = cur;
+        cur = next;
+    }
+}
+
+// ---- metrics (LogCurrentMetrics, FluidSim.cs:582-594): sum of density, max |V| -------------------------
+__global__ void __launch_bounds__(256)
+metrics_kernel(const float *__restrict__ d, const float *__restrict__ ux, const float *__restrict__ uy,
+               const float *__restrict__ uz, long long n, long long per, double *sum, unsigned int *mx) {
+    double acc = 0.0;
+    float m = 0.0f;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (long long r = 0; r < per && t < n; r++, t += stride) {
+        acc += (double)d[t];
+        float q = ux[t] * ux[t] + uy[t] * uy[t];
+        if (uz) q = q + uz[t] * uz[t];
+        m = fmaxf(m, sqrtf(q));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    __shared__ double s_acc[8];
+    __shared__ float s_m[8];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { s_acc[w] = acc; s_m[w] = m; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 8; i++) { acc += s_acc[i]; m = fmaxf(m, s_m[i]); }
+        atomicAdd(sum, acc);
+        atomicMax(mx, __float_as_uint(m)); // non-negative floats order like their bit patterns
+    }
+}

@@ -1,0 +1,220 @@
+"""Host-side mirror of the reference's ``FluidSimulation`` MonoBehaviour for the solver hot path.
+
+The reference's host language is C# (Unity); no C# toolchain exists in the build image, so the
+compiled-language host is ``Assets/Plugin/FluidSimulationNative.cs`` (written against the same C
+ABI, not compilable here) and THIS module is the host side that the tests and the benchmark drive.
+It keeps the reference's field names, argument meanings and call order
+(Assets/Scripts/FluidSim.cs: public fields :12-110, Update :390-450, Simulate :551-576,
+AddDensity/AddVelocity :723-738, UpdateCustomSource :485-533, AddForceToArea :452-483,
+SetupObstacles :302-388, ResetSimulation :213-235).
+
+Everything numerical happens in libfluidsolver.so (CUDA); this file only does what the reference
+does on the managed side: parameter scaling, source lists, the obstacle mask.
+"""
+from __future__ import annotations
+
+import math
+from collections import deque
+
+import numpy as np
+
+from . import native
+
+f32 = np.float32
+
+
+def _round_half_even(v: float) -> int:
+    """Mathf.RoundToInt: banker's rounding on the float value."""
+    return int(np.rint(f32(v)))
+
+
+class FluidSimulation:
+    """Drop-in for the reference component's solver surface.  ``depth`` (nz) is the 3D extension:
+    ``depth=1`` reproduces the reference's 2D solver."""
+
+    # FluidSim.cs:19-31 defaults
+    def __init__(self, size=128, resolutionMultiplier=1.0, *, depth=1, physicalSize=1.0, diffusion=1e-4,
+                 viscosity=1e-4, timeStep=0.1, autoAdjustParameters=True, enableObstacle=True,
+                 obstacleShape="Circle", obstaclePositionX=0.5, obstaclePositionY=0.5, obstaclePositionZ=0.5,
+                 obstacleRadius=0.1, obstacleWidth=0.2, obstacleHeight=0.2, itersDiffuse=20, itersPressure=20,
+                 solverKind=native.JACOBI, device_id=0, use_cuda_graph=True, lib_path=None):
+        self.paused = False
+        self.size, self.resolutionMultiplier, self.depth = size, resolutionMultiplier, depth
+        self.physicalSize, self.diffusion, self.viscosity, self.timeStep = physicalSize, diffusion, viscosity, timeStep
+        self.autoAdjustParameters = autoAdjustParameters
+        # customizable source, :34-55
+        self.enableCustomSource = False
+        self.sourceStrength, self.sourceEmitsVelocity, self.sourceDirection = 100.0, False, 0.0
+        self.sourceVelocity, self.sourceRadius, self.sourcePulseRate, self.sourcePulsing = 10.0, 1.0, 1.0, False
+        self.sourcePositionX, self.sourcePositionY, self.sourcePositionZ = 0.5, 0.5, 0.5
+        # obstacle, :96-110
+        self.enableObstacle, self.obstacleShape = enableObstacle, obstacleShape
+        self.obstaclePositionX, self.obstaclePositionY, self.obstaclePositionZ = obstaclePositionX, obstaclePositionY, obstaclePositionZ
+        self.obstacleRadius, self.obstacleWidth, self.obstacleHeight = obstacleRadius, obstacleWidth, obstacleHeight
+        self.itersDiffuse, self.itersPressure, self.solverKind = itersDiffuse, itersPressure, solverKind
+        self._device_id, self._use_graph, self._lib_path = device_id, use_cuda_graph, lib_path
+        self.elapsedTime = 0.0
+        self.native: native.NativeSolver | None = None
+        self.ResetSimulation()
+
+    # ---- ResetSimulation, :213-235 (+ SetupObstacles :299) -------------------------------------
+    def ResetSimulation(self):
+        self.currentSize = _round_half_even(self.size * self.resolutionMultiplier)   # :216
+        self.cellSize = f32(self.physicalSize) / f32(self.currentSize)               # :219
+        self.dtScale = f32(128.0) / f32(self.currentSize) if self.autoAdjustParameters else f32(1.0)  # :222
+        n = self.currentSize
+        self.currentDepth = 1 if self.depth == 1 else _round_half_even(self.depth * self.resolutionMultiplier)
+        if self.native is not None:
+            self.native.close()
+        self.native = native.NativeSolver(
+            n, n, self.currentDepth, iters_diffuse=self.itersDiffuse, iters_pressure=self.itersPressure,
+            solver_kind=self.solverKind, enable_obstacle=self.enableObstacle, cell_size=float(self.cellSize),
+            raw_viscosity=self.viscosity, device_id=self._device_id, use_cuda_graph=self._use_graph,
+            lib_path=self._lib_path)
+        shape = (n, n) if self.currentDepth == 1 else (self.currentDepth, n, n)
+        self.obstacles = np.zeros(shape, np.uint8)
+        self.SetupObstacles()
+
+    def SetPaused(self, Paused: bool):  # :149
+        self.paused = Paused
+
+    def GetSourcePosition(self):  # :979
+        return (self.sourcePositionX * self.currentSize, self.sourcePositionY * self.currentSize)
+
+    def SetSourcePosition(self, x, y):  # :984
+        self.sourcePositionX = min(max(x / self.currentSize, 0.0), 1.0)
+        self.sourcePositionY = min(max(y / self.currentSize, 0.0), 1.0)
+
+    # ---- SetupObstacles / RecursiveFloodFill / IsInsideShape, :302-388 ---------------------------
+    def _inside(self, x, y, size):
+        n = self.currentSize
+        cx, cy = f32(self.obstaclePositionX * n), f32(self.obstaclePositionY * n)
+        if self.obstacleShape == "Circle":
+            return f32(x - cx) * f32(x - cx) + f32(y - cy) * f32(y - cy) < f32(size) * f32(size)
+        if self.obstacleShape == "Rectangle":
+            hw, hh = f32(self.obstacleWidth * n * 0.5), f32(self.obstacleHeight * n * 0.5)
+            return (cx - hw) < x < (cx + hw) and (cy - hh) < y < (cy + hh)
+        if self.obstacleShape == "Airfoil":  # approximate NACA 0015, :369-383
+            chord = f32(2 * self.obstacleWidth * n)
+            t = f32(0.15)
+            nx_ = f32(x - cx + chord / 2) / chord
+            ny_ = f32(y - cy) / chord
+            if nx_ < 0 or nx_ > 1 or abs(ny_) > t:
+                return False
+            half = 5 * t * (f32(0.2969) * f32(math.sqrt(nx_)) - f32(0.1260) * nx_ - f32(0.3516) * nx_ * nx_
+                            + f32(0.2843) * nx_ ** 3 - f32(0.1015) * nx_ ** 4)
+            return abs(ny_) <= half
+        return False
+
+    def SetupObstacles(self):
+        n = self.currentSize
+        m2 = np.zeros((n, n), np.uint8)
+        if self.enableObstacle:
+            sx, sy = _round_half_even(self.obstaclePositionX * n), _round_half_even(self.obstaclePositionY * n)
+            size = (self.obstacleRadius if self.obstacleShape == "Circle" else self.obstacleWidth) * n  # :316-324
+            todo = deque([(sx, sy)])  # iterative form of the recursive 4-neighbour flood fill
+            while todo:
+                x, y = todo.pop()
+                if x < 0 or x >= n or y < 0 or y >= n or m2[y, x] or not self._inside(x, y, size):
+                    continue
+                m2[y, x] = 1
+                todo.extend(((x + 1, y), (x - 1, y), (x, y + 1), (x, y - 1)))
+        if self.currentDepth == 1:
+            self.obstacles = m2
+        else:
+            # 3D extension: circle -> sphere, other shapes extruded in z
+            nz = self.currentDepth
+            m3 = np.zeros((nz, n, n), np.uint8)
+            if self.enableObstacle:
+                if self.obstacleShape == "Circle":
+                    r = f32(self.obstacleRadius * n)
+                    z, y, x = np.meshgrid(np.arange(nz, dtype=f32), np.arange(n, dtype=f32), np.arange(n, dtype=f32), indexing="ij")
+                    cx, cy, cz = f32(self.obstaclePositionX * n), f32(self.obstaclePositionY * n), f32(self.obstaclePositionZ * nz)
+                    m3 = (((x - cx) ** 2 + (y - cy) ** 2 + (z - cz) ** 2) < r * r).astype(np.uint8)
+                else:
+                    half = max(1, int(self.obstacleWidth * nz * 0.5))
+                    c = _round_half_even(self.obstaclePositionZ * nz)
+                    m3[max(c - half, 0):min(c + half, nz)] = m2
+            self.obstacles = m3
+        self.native.set_obstacles(self.obstacles)
+
+    # ---- sources -----------------------------------------------------------------------------------
+    def AddDensity(self, x, y, amount, z=0.0):  # :723-729
+        self.native.add_density(x, y, z, amount)
+
+    def AddVelocity(self, x, y, amountX, amountY, z=0.0, amountZ=0.0):  # :731-738
+        self.native.add_velocity(x, y, z, amountX, amountY, amountZ)
+
+    def UpdateCustomSource(self):
+        """:485-533 -- the disc of AddDensity/AddVelocity calls, sent as one batched native call."""
+        n = self.currentSize
+        sx, sy = f32(self.sourcePositionX * n), f32(self.sourcePositionY * n)
+        pulse = abs(math.sin(self.elapsedTime * self.sourcePulseRate * math.pi)) if self.sourcePulsing else 1.0
+        strength = f32(self.sourceStrength * pulse) * f32(self.resolutionMultiplier)
+        rad = f32(self.sourceRadius * self.resolutionMultiplier)
+        xs, ys, ds, ax, ay = [], [], [], [], []
+        for i in range(max(0, math.floor(sx - rad)), min(n - 1, math.ceil(sx + rad)) + 1):
+            for j in range(max(0, math.floor(sy - rad)), min(n - 1, math.ceil(sy + rad)) + 1):
+                dist = f32(math.sqrt(f32((i - sx) * (i - sx) + (j - sy) * (j - sy))))
+                if dist <= rad:
+                    fall = f32(1.0) - dist / rad
+                    xs.append(i); ys.append(j); ds.append(strength * fall)
+                    if self.sourceEmitsVelocity:
+                        ang = f32(self.sourceDirection) * f32(math.pi / 180.0)
+                        ax.append(f32(math.cos(ang)) * f32(self.sourceVelocity) * f32(self.resolutionMultiplier) * fall)
+                        ay.append(f32(math.sin(ang)) * f32(self.sourceVelocity) * f32(self.resolutionMultiplier) * fall)
+        if xs:
+            z = [self.sourcePositionZ * self.currentDepth] * len(xs) if self.currentDepth > 1 else None
+            self.native.add_source_cells(xs, ys, z, ds, ax or None, ay or None, None)
+
+    def AddForceToArea(self, center, force, radius):
+        """:452-483 -- mouse drag: velocity with linear fall-off, density inside 0.3 r."""
+        n = self.currentSize
+        cx, cy = center
+        clamp = lambda v: min(max(v, 0), n - 1)
+        xs, ys, ds, ax, ay = [], [], [], [], []
+        for x in range(clamp(int(cx - radius)), clamp(int(cx + radius)) + 1):
+            for y in range(clamp(int(cy - radius)), clamp(int(cy + radius)) + 1):
+                dist = f32(math.sqrt(f32((x - cx) ** 2 + (y - cy) ** 2)))
+                if dist <= radius:
+                    fall = f32(1) - dist / f32(radius)
+                    xs.append(x); ys.append(y); ax.append(f32(force[0]) * fall); ay.append(f32(force[1]) * fall)
+                    ds.append(f32(self.sourceStrength) * fall if dist < radius * 0.3 else f32(0))
+        if xs:
+            self.native.add_source_cells(xs, ys, None, ds, ax, ay, None)
+
+    # ---- Simulate / Update, :390-450, :551-576 --------------------------------------------------------
+    def effective_parameters(self):
+        """:554-556"""
+        if self.autoAdjustParameters:
+            return (float(f32(self.timeStep) * self.dtScale), float(f32(self.viscosity) / f32(self.resolutionMultiplier)),
+                    float(f32(self.diffusion) / f32(self.resolutionMultiplier)))
+        return float(self.timeStep), float(self.viscosity), float(self.diffusion)
+
+    def Simulate(self):
+        dt, visc, diff = self.effective_parameters()
+        self.native.step(dt, visc, diff)
+
+    Step = Simulate
+
+    def Update(self, deltaTime=1.0 / 60):
+        """:390-450 without input/visualisation: sources first, then the step."""
+        if self.paused:
+            return
+        self.elapsedTime += deltaTime
+        if self.enableCustomSource:
+            self.UpdateCustomSource()
+        self.Simulate()
+
+    # ---- readers (what UpdateVisualization/LogCurrentMetrics pull, :587-594, :761-768) -------------------
+    def field(self, name):
+        return self.native.get_field(name)
+
+    def metrics(self):
+        mean, mx, _ = self.native.metrics()
+        return mean, mx
+
+    def close(self):
+        if self.native is not None:
+            self.native.close()
+            self.native = None

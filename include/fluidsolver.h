@@ -1,0 +1,159 @@
+/*
+ * fluidsolver.h -- C ABI of libfluidsolver.so, the B200 (sm_100a) native plugin that replaces the
+ * solver hot path of ChrisWangstpauls/3DFluidSimulation (Assets/Scripts/FluidSim.cs).
+ *
+ * The reference has no plugin boundary for the solver: it is private methods on a MonoBehaviour.
+ * The boundary is therefore cut at the reference's internal seam: every
+ * entry point below names the FluidSim.cs member(s) it replaces.  Plain C types only; cdecl; the
+ * library never throws across the ABI.  The reference-side binding (C# P/Invoke) is
+ * Assets/Plugin/NativeFluidSolver.cs, described in INTEGRATION.md.
+ *
+ * Conventions
+ *   - return value: FS_OK (0) or a negative fs_status; fs_last_error() gives the message.
+ *   - layout: fp32, idx = x + y*nx + z*nx*ny (FluidSim.cs:749-752 plus a z stride).
+ *   - nz == 1 selects the reference's 2D solver exactly (z terms skipped, coefficients unchanged).
+ *   - "N" (the reference's `size`/`currentSize`) is nx.
+ *   - host pointers are only read/written during the call; the plugin owns all device memory.
+ *   - one host thread per handle; distinct handles are independent.
+ *   - fs_step is asynchronous (returns after enqueueing); fs_get_* / fs_sync synchronise.
+ */
+#ifndef FLUIDSOLVER_H
+#define FLUIDSOLVER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FS_ABI_VERSION 1
+
+typedef enum fs_status {
+    FS_OK = 0,
+    FS_ERR_BAD_ARGUMENT = -1,
+    FS_ERR_CUDA = -2,
+    FS_ERR_OUT_OF_MEMORY = -3,
+    FS_ERR_UNSUPPORTED = -4,
+    FS_ERR_COMM = -5
+} fs_status;
+
+/* Field ids for fs_get_field / fs_set_field.  FluidSim.cs:112-117 (+ z components). */
+typedef enum fs_field {
+    FS_DENSITY = 0,  /* density      :112 */
+    FS_VX = 1,       /* velocityX    :113 */
+    FS_VY = 2,       /* velocityY    :114 */
+    FS_VZ = 3,       /* (3D only) */
+    FS_VX0 = 4,      /* velocityX0   :115  scratch: contents after fs_step are unspecified */
+    FS_VY0 = 5,      /* velocityY0   :116  scratch */
+    FS_VZ0 = 6,      /* scratch */
+    FS_PRESSURE = 7, /* pressure     :117, written by ProjectWithJobs :1509 */
+    FS_DIVERGENCE = 8, /* nativeDiv of the last projection (:1428), for diagnostics/tests */
+    FS_FIELD_COUNT = 9
+} fs_field;
+
+typedef enum fs_solver_kind {
+    FS_JACOBI = 0,    /* the reference's double-buffered relaxation (FluidSim.cs:1188-1233) */
+    FS_RED_BLACK = 1  /* red-black Gauss-Seidel for the pressure solve (BASELINE config 5) */
+} fs_solver_kind;
+
+/* Creation parameters.  Replaces ResetSimulation's sizing/allocation, FluidSim.cs:213-235. */
+typedef struct fs_params {
+    int32_t abi_version;     /* must be FS_ABI_VERSION */
+    int32_t nx, ny, nz;      /* GLOBAL grid; the reference uses nx == ny == currentSize, nz == 1 */
+    int32_t iters_diffuse;   /* iterations of each Diffuse pass; 20 in the reference (:1310, :1378) */
+    int32_t iters_pressure;  /* iterations of the pressure solve; 20 in the reference (:1594) */
+    int32_t solver_kind;     /* fs_solver_kind */
+    int32_t enable_obstacle; /* FluidSim.cs:97, :567: run the obstacle post-pass inside fs_step */
+    float cell_size;         /* FluidSim.cs:219  physicalSize / currentSize */
+    float raw_viscosity;     /* FluidSim.cs:664: the drag uses the UNSCALED viscosity */
+    int32_t device_id;       /* CUDA device ordinal of this handle */
+    int32_t slab_rank;       /* z-slab decomposition: this handle owns slab slab_rank ... */
+    int32_t slab_count;      /* ... of slab_count (1 = whole grid on one GPU) */
+    int32_t use_cuda_graph;  /* 1: capture fs_step's launch sequence in a CUDA graph and replay it */
+    int32_t reserved[4];     /* must be 0 */
+} fs_params;
+
+typedef struct fs_solver fs_solver; /* opaque */
+
+/* ---- lifetime: ResetSimulation/ResetJobBuffers/OnDestroy, FluidSim.cs:213-235, :990-1032 ---- */
+int fs_create(const fs_params *params, fs_solver **out);
+void fs_destroy(fs_solver *s);
+int fs_reset(fs_solver *s); /* all fields and the mask to zero (:225-232) */
+const char *fs_last_error(const fs_solver *s); /* s may be NULL: error of the last failed fs_create */
+int fs_abi_version(void);
+
+/* ---- geometry of this handle's slab ----------------------------------------------------------- */
+/* Owned global z range [z_begin, z_end) and the number of owned voxels nx*ny*(z_end-z_begin). */
+int fs_slab_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end, int64_t *owned_voxels);
+
+/* ---- obstacles: SetupObstacles writes bool[] obstacles, FluidSim.cs:302-327 -------------------
+ * mask: one byte per cell of the GLOBAL grid (0 = fluid), n = nx*ny*nz.  C# bool[] is not
+ * blittable: pass byte[]. */
+int fs_set_obstacles(fs_solver *s, const uint8_t *mask, int64_t n);
+
+/* ---- sources: AddDensity / AddVelocity, FluidSim.cs:723-738 (cell = clamp((int)coord)) --------
+ * Global coordinates; a handle ignores cells outside its slab.  z, az ignored when nz == 1. */
+int fs_add_density(fs_solver *s, float x, float y, float z, float amount);
+int fs_add_velocity(fs_solver *s, float x, float y, float z, float ax, float ay, float az);
+/* Batched form of the loops in UpdateCustomSource/AddForceToArea (FluidSim.cs:452-533): count
+ * cells, arrays of length count (vx/vy/vz/density amounts may be NULL). */
+int fs_add_source_cells(fs_solver *s, int64_t count, const float *x, const float *y, const float *z,
+                        const float *density, const float *ax, const float *ay, const float *az);
+/* Dense add: field[i] += src[i] over this handle's OWNED voxels (any pointer may be NULL). */
+int fs_add_sources(fs_solver *s, const float *density, const float *vx, const float *vy, const float *vz);
+
+/* ---- the step: Simulate(), FluidSim.cs:551-570 = VelocityStep :703-714 + DensityStep :716-721
+ * + EnforceObstacleBoundaries :617-673 when enable_obstacle.  dt/visc/diff are the already scaled
+ * effective values of :554-556 (the scaling stays on the C# side). */
+int fs_step(fs_solver *s, float dt, float visc, float diff);
+int fs_sync(fs_solver *s);
+
+/* ---- field access: what UpdateVisualization / DrawStreamlines / tests read (:761-768, :919) ----
+ * n must equal the handle's owned voxel count; planes are in global z order. */
+int fs_get_field(fs_solver *s, int32_t field, float *out, int64_t n);
+int fs_set_field(fs_solver *s, int32_t field, const float *in, int64_t n);
+
+/* ---- metrics: LogCurrentMetrics, FluidSim.cs:582-594 (mean density, max |V|) over owned voxels;
+ * sum_density is returned so that slabs can be combined. */
+int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density);
+
+/* ---- operator entry points (one reference job chain each) --------------------------------------
+ * They act on the handle's fields and are what the parity tests drive kernel by kernel.
+ *   fs_op_set_bnd       BoundaryJob                          :1235-1289
+ *   fs_op_diffuse       Diffuse = DiffuseWithJobs + LinearSolveWithJobs   :740-745, :1292-1415
+ *   fs_op_smooth        DiffuseWithJobs only (pass 1)        :1292-1357
+ *   fs_op_lin_solve     LinearSolveWithJobs only (pass 2)    :1359-1415 (dst holds the initial guess)
+ *   fs_op_project       ProjectWithJobs on (vx,vy,vz) fields :1417-1521 (+ :1578-1637)
+ *   fs_op_advect        AdvectWithJobs                       :1523-1576
+ *   fs_op_enforce_obstacles  EnforceObstacleBoundaries       :617-673
+ * b: 0 scalar, 1/2/3 velocity component.  dst/src are fs_field ids; dst != src. */
+int fs_op_set_bnd(fs_solver *s, int32_t field, int32_t b);
+int fs_op_diffuse(fs_solver *s, int32_t dst, int32_t src, int32_t b, float diff, float dt);
+int fs_op_smooth(fs_solver *s, int32_t dst, int32_t src, int32_t b, float a, float c, int32_t iters);
+int fs_op_lin_solve(fs_solver *s, int32_t dst, int32_t rhs, int32_t b, float a, float c, int32_t iters,
+                    int32_t solver_kind);
+int fs_op_project(fs_solver *s, int32_t use_v0_fields); /* 0: (VX,VY,VZ); 1: (VX0,VY0,VZ0) */
+int fs_op_advect(fs_solver *s, int32_t dst, int32_t src, int32_t b, int32_t use_v0_fields, float dt);
+int fs_op_advect_velocity(fs_solver *s, float dt); /* (VX,VY,VZ) <- advect (VX0,VY0,VZ0) along itself, :710-711 */
+int fs_op_enforce_obstacles(fs_solver *s);
+
+/* ---- measurement helpers (CUDA events on the solver's own stream) ------------------------------ */
+int fs_timer_start(fs_solver *s);
+int fs_timer_stop(fs_solver *s, float *elapsed_ms); /* records, synchronises, returns the interval */
+int64_t fs_launch_count(const fs_solver *s);        /* kernels launched by this handle so far */
+/* Average duration of `reps` back-to-back launches of one relaxation sweep (kind 0 = pass-1
+ * smoother, 1 = Jacobi, 2 = red-black full sweep) on scratch fields; fills the algorithmic bytes per launch. */
+int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes);
+
+/* ---- multi-GPU wiring (z-slabs, one handle per GPU) ------------------- */
+#define FS_IPC_BLOB_BYTES 1024
+/* Export this handle's halo mailbox as an opaque blob (CUDA IPC handles inside). */
+int fs_halo_export(fs_solver *s, void *blob, int64_t blob_bytes);
+/* Connect the lower (slab_rank-1) and upper (slab_rank+1) neighbours; NULL for none. same_process=1
+ * when the neighbour handle lives in this process (pointers are passed instead of IPC handles). */
+int fs_halo_connect(fs_solver *s, const void *lower_blob, const void *upper_blob, int32_t same_process);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUIDSOLVER_H */

@@ -1,0 +1,149 @@
+"""GPU tier (`-m gpu`): the parity tests proper.  Everything goes through the C ABI of the real
+libfluidsolver.so (CUDA kernels on cuda:0) and is compared with the oracle on the same seeded inputs,
+with the committed golden fixtures, and -- at BASELINE.json's full sizes -- through size-independent
+properties."""
+import os
+
+import numpy as np
+import pytest
+
+import parity_cases as P
+
+pytestmark = pytest.mark.gpu
+
+# nx % 4 == 0 takes the float4 z-marching kernel (relax_vec4); other nx take the per-cell kernels
+GRIDS = [(16, 12, 1), (64, 48, 1), (30, 30, 1), (4, 4, 1), (16, 12, 9), (64, 40, 35), (30, 17, 11), (4, 3, 3),
+         (8, 3, 3), (132, 20, 70)]
+
+
+@pytest.fixture(scope="module")
+def lib(cuda_lib):
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tier needs a CUDA device"
+    return cuda_lib
+
+
+@pytest.mark.parametrize("dims", GRIDS)
+def test_set_bnd(lib, oracle, dims):
+    P.case_set_bnd(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", GRIDS)
+@pytest.mark.parametrize("obstacles", [True, False])
+def test_smooth_linsolve_diffuse(lib, oracle, dims, obstacles):
+    P.case_smooth_and_linsolve(lib, oracle, *dims, obstacles=obstacles)
+
+
+@pytest.mark.parametrize("dims", GRIDS)
+def test_project(lib, oracle, dims):
+    P.case_project(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", GRIDS)
+def test_advect(lib, oracle, dims):
+    P.case_advect(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", [(16, 12, 1), (64, 40, 35)])
+def test_enforce(lib, oracle, dims):
+    P.case_enforce(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", [(16, 12, 1), (16, 12, 9)])
+def test_sources(lib, oracle, dims):
+    P.case_sources(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("name", ["kernels2d_n24.npz", "kernels2d_n30.npz"])
+def test_golden_kernels(lib, name):
+    P.case_golden_2d(lib, name)
+
+
+@pytest.mark.parametrize("name", ["traj2d_n32_obst.npz", "traj2d_n32_free.npz"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_golden_trajectory(lib, name, graph):
+    P.case_golden_trajectory(lib, name, use_graph=graph)
+
+
+@pytest.mark.parametrize("obstacles", [True, False])
+def test_config1_32cube_trajectory(lib, oracle, obstacles):
+    """BASELINE config 1: 32^3 smoke plume, K_d = K_p = 20, dt = 0.1 (10 steps here, CFL <~ 3)."""
+    P.case_steps(lib, oracle, 32, 32, 32, 10, kd=20, kp=20, obstacles=obstacles, use_graph=True)
+
+
+def test_config2_128cube_single_step(lib, oracle):
+    """BASELINE config 2: 128^3, 40 pressure iterations, field-by-field check after 1 and 2 steps."""
+    P.case_steps(lib, oracle, 128, 128, 128, 2, kd=20, kp=40, obstacles=True, use_graph=True, dt=0.1 * 128 / 128)
+
+
+def test_scene_configs_2d(lib, oracle):
+    """The two scene parameter sets (SampleScene.unity): 192^2 and 128^2, 3 steps each."""
+    P.case_steps(lib, oracle, 192, 192, 1, 3, obstacles=True, dt=0.1 * 128 / 192, visc=1e-4 / 3, diff=1e-4 / 3)
+    P.case_steps(lib, oracle, 128, 128, 1, 3, obstacles=True)
+
+
+def test_red_black_matches_oracle(lib, oracle):
+    rng = np.random.default_rng(9)
+    shape = (10, 9, 12)
+    mask = P.random_mask(shape, rng)
+    rhs, guess = P.rnd(shape, rng), P.rnd(shape, rng)
+    with P.make_solver(lib, 12, 9, 10) as s:
+        s.set_obstacles(mask)
+        for b in (0, 1, 3):
+            s.set_field("vx", rhs); s.set_field("vy0", guess)
+            s.op_lin_solve("vy0", "vx", b, 0.3, 2.8, 4, solver_kind=1)
+            P.assert_exact(s.get_field("vy0"), oracle.lin_solve(b, guess, rhs, 0.3, 2.8, mask, 4, red_black=True), f"rb b={b}")
+
+
+def test_vector_and_scalar_kernels_agree(lib, oracle):
+    """relax_vec4 against the per-cell kernels (FS_FORCE_GENERIC=1) on a grid the oracle would take
+    minutes for: 256^3, full step, bit-identical fields."""
+    def run(force):
+        os.environ["FS_FORCE_GENERIC"] = "1" if force else "0"
+        try:
+            s, _ = None, None
+            pk = P.pkg()
+            s = pk.NativeSolver(256, 256, 256, iters_diffuse=4, iters_pressure=6, enable_obstacle=False, lib_path=lib)
+            rng = np.random.default_rng(11)
+            for n in ("density", "vx", "vy", "vz"):
+                s.set_field(n, P.rnd((256, 256, 256), rng, 0.5))
+            s.step(0.02, 1e-3, 1e-3)
+            out = {n: s.get_field(n) for n in ("density", "vx", "vy", "vz", "pressure")}
+            s.close()
+            return out
+        finally:
+            os.environ.pop("FS_FORCE_GENERIC", None)
+    a, b = run(False), run(True)
+    for n in a:
+        P.assert_exact(a[n], b[n], f"vec4 vs per-cell {n}")
+
+
+def test_full_size_properties_512(lib):
+    """BASELINE config 4 size (512^3, K_p = 80): properties that need no oracle run.
+    (1) a uniform density with zero velocity stays exactly uniform through a full step (3D stencil
+    preserves constants; advect with V = 0 is the identity); (2) with zero velocity the pressure and
+    divergence are identically zero; (3) mirror symmetry: a y-symmetric plume stays y... x-symmetric."""
+    pk = P.pkg()
+    n = 512
+    s = pk.NativeSolver(n, n, n, iters_diffuse=20, iters_pressure=80, enable_obstacle=False, lib_path=lib, use_cuda_graph=True)
+    d = np.full((n, n, n), 2.5, np.float32)
+    s.set_field("density", d)
+    s.step(0.025, 1e-4, 1e-4)
+    got = s.get_field("density")
+    assert float(np.abs(got - 2.5).max()) <= 2.5 * 3e-6          # (1+6a)/(1+6a) rounding only
+    assert not s.get_field("pressure").any() and not s.get_field("divergence").any()
+    # x-mirror symmetry of a centred plume: density(x) == density(n-1-x), vx antisymmetric
+    s.reset()
+    zz, yy, xx = np.meshgrid(np.arange(8), np.arange(8), np.arange(8), indexing="ij")
+    blob = np.zeros((n, n, n), np.float32)
+    c = n // 2
+    blob[c - 4:c + 4, 100:108, c - 4:c + 4] = 50.0
+    vy = np.zeros_like(blob); vy[c - 4:c + 4, 100:108, c - 4:c + 4] = 2.0
+    s.set_field("density", blob); s.set_field("vy", vy)
+    s.step(0.025, 1e-4, 1e-4)
+    dd, vx = s.get_field("density"), s.get_field("vx")
+    assert dd.any()
+    np.testing.assert_allclose(dd, dd[:, :, ::-1], rtol=0, atol=1e-5 * float(dd.max()))
+    np.testing.assert_allclose(vx, -vx[:, :, ::-1], rtol=0, atol=1e-5 * max(float(np.abs(vx).max()), 1e-20))
+    s.close()
