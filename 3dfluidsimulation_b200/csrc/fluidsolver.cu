@@ -156,15 +156,20 @@ struct CudaExec {
         if (cnt <= 0) return;
         if (g.nx % 4 == 0 && !force_generic) {
             const int groups = g.nx / 4;
+            // small grids: smaller CTAs so that there are enough of them to occupy 148 SMs
+            const long long thread_planes = (long long)groups * (g.ny - 2) * cnt;
+            const int threads = thread_planes >= (long long)sm_count * 256 * 16 ? 256 : 64;
             int bx = 32;
             while (bx / 2 >= groups && bx > 1) bx /= 2;
-            const int by = 256 / bx;
+            const int by = threads / bx;
             const int gxn = (groups + bx - 1) / bx, gyn = (g.ny - 2 + by - 1) / by;
             const long long blocks_xy = (long long)gxn * gyn;
-            const long long target = (long long)sm_count * 16; // >= 2 waves at 8 resident CTAs per SM
+            // z chunk per CTA: short enough for >= ~4 waves of 4 resident CTAs/SM (tail effect), long enough
+            // that re-reading the two halo planes per chunk stays <= 2/16 of one field
+            const long long target = (long long)sm_count * 16;
             long long zchunk = (long long)cnt * blocks_xy / target;
-            if (zchunk < 16) zchunk = 16;
-            if (zchunk > 64) zchunk = 64;
+            if (zchunk < 4) zchunk = 4;
+            if (zchunk > 16) zchunk = 16;
             if (zchunk > cnt) zchunk = cnt;
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
             const dim3 block(bx, by, 1), grid(gxn, gyn, nchunks);
@@ -271,6 +276,17 @@ struct CudaExec {
         FS_CUDA(cudaMemcpyAsync(&bits, d_max, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
         FS_CUDA(cudaStreamSynchronize(st));
         memcpy(mx, &bits, sizeof(float));
+    }
+
+    unsigned long long division_selftest(float c, unsigned long long first, unsigned long long count) {
+        unsigned long long *d = (unsigned long long *)get_scratch(sizeof(unsigned long long));
+        unsigned long long h = 0;
+        FS_CUDA(cudaMemsetAsync(d, 0, sizeof(h), st));
+        division_selftest_kernel<<<sm_count * 8, 256, 0, st>>>(c, first, count, d);
+        launches++;
+        FS_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        return h;
     }
 
     // ---- halo exchange (z-slabs) ---------------------------------------------------------------------

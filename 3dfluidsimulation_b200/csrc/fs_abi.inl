@@ -222,6 +222,13 @@ int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *a
     return c.check();
 }
 
+int fs_selftest_division(fs_solver *s, float divisor, uint64_t first_bits, uint64_t count, uint64_t *mismatches) {
+    FS_GUARD(s);
+    if (!mismatches) return c.fail(FS_ERR_BAD_ARGUMENT, "null argument");
+    *mismatches = c.ex.division_selftest(divisor, first_bits, count);
+    return c.check();
+}
+
 // ---- multi-GPU wiring ------------------------------------------------------------------------------------
 int fs_halo_export(fs_solver *s, void *blob, int64_t blob_bytes) {
     FS_GUARD(s);

@@ -49,12 +49,64 @@ __device__ __forceinline__ void st4(float *p, const float v[4]) {
     *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// ---- correctly rounded division by a launch-constant divisor ------------------------------------------
+// `x / c` compiles to div.rn.f32, whose FCHK guard sends zero / denormal numerators to a ~40 instruction
+// slow path -- and a smoke-plume field is exactly zero or denormal almost everywhere (profiles/r01a_*:
+// every division took the slow path, the sweep was issue bound at 41% of DRAM peak).  For a constant
+// divisor the quotient can be had without any data-dependent path: y = RN(1/c) once per thread, then
+//   q0 = RN(n*y); r0 = n - c*q0; q1 = RN(q0 + r0*y)   (q1 is a faithful rounding of n/c)
+//   r1 = n - c*q1 (exact, FMA);  q2 = RN(q1 + r1*y)   == RN(n/c)  (Markstein's theorem: y correctly
+// rounded, q1 faithful, no under/overflow).  Numerators whose exponent is outside [2^-100, 2^101) --
+// denormals, huge values, inf/nan -- take the IEEE division, zero keeps its sign via n*y.  Divisors outside
+// [2^-20, 2^20] disable the fast path altogether.  fs_selftest_division() checks fs_div against
+// __fdiv_rn bit for bit over any range of numerator bit patterns (tests run all 2^32 of them).
+struct FsDivisor {
+    float c, rc;
+    int safe;
+};
+__device__ __forceinline__ FsDivisor fs_make_divisor(float c) {
+    FsDivisor d;
+    d.c = c;
+    d.rc = __frcp_rn(c);
+    const float ac = fabsf(c);
+    d.safe = (ac >= 9.5367431640625e-07f && ac <= 1048576.0f) ? 1 : 0;
+    return d;
+}
+__device__ __forceinline__ float fs_div(float n, const FsDivisor &d) {
+    const float q0 = __fmul_rn(n, d.rc);
+    const float r0 = __fmaf_rn(-d.c, q0, n);
+    const float q1 = __fmaf_rn(r0, d.rc, q0);
+    const float r1 = __fmaf_rn(-d.c, q1, n);
+    float q2 = __fmaf_rn(r1, d.rc, q1);
+    const unsigned e = (__float_as_uint(n) >> 23) & 0xffu;
+    if (e - 27u > 200u) {                       // zero, denormal, tiny, huge, inf, nan
+        if (n == 0.0f) q2 = q0;                 // signed zero, as n / c
+        else q2 = __fdiv_rn(n, d.c);
+    }
+    return q2;
+}
+
+__global__ void __launch_bounds__(256)
+division_selftest_kernel(float c, unsigned long long first, unsigned long long count, unsigned long long *mismatches) {
+    const FsDivisor d = fs_make_divisor(c);
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    unsigned long long bad = 0;
+    for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < count; t += stride) {
+        const float n = __uint_as_float((unsigned)(first + t));
+        const float want = __fdiv_rn(n, c);
+        const float got = d.safe ? fs_div(n, d) : want;
+        const bool both_nan = (want != want) && (got != got);
+        if (!both_nan && __float_as_uint(want) != __float_as_uint(got)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ---- the hot sweep ---------------------------------------------------------------------------------
 // Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
 // kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
 template <int MODE, bool HZ>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
            const int in_zero, const int kl_begin, const int kl_end, const int zchunk) {
@@ -66,9 +118,14 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     const int k_hi = min(k_lo + zchunk, kl_end);
     if (k_lo >= k_hi) return;
 
+    const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
     const int fxl[4] = {first_x ? 1 : 0, 0, 0, last_x ? 1 : 0};
     const float *stale_src = stale ? stale : out;
+    // extra ring rows this thread owns in y (set_bnd faces/edges), -1 = none
+    const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
+    const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1; // ny == 3: both
+    const bool xy_plain = !first_x && !last_x && jr < 0;
 
     long long idx = fs_idx(g, x0, j, k_lo);
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
@@ -95,41 +152,47 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
         const float nxv[4] = {next.x, next.y, next.z, next.w}, pvv[4] = {prev.x, prev.y, prev.z, prev.w};
         const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
-        float st[4] = {0.f, 0.f, 0.f, 0.f};
-        if (MODE == FS_MODE_SMOOTH && (fl & 0x01010101u)) {
-            const float4 s4 = ld4_plain(stale_src + idx);
-            st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
-        }
         float v[4];
 #pragma unroll
         for (int l = 0; l < 4; l++) {
-            const bool obst = (fl >> (8 * l)) & 1u;
             float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
             if (HZ) s = (s + nxv[l]) + pvv[l];
-            const float val = (rv[l] + a * s) / c;
-            v[l] = obst ? (MODE == FS_MODE_JACOBI ? cv[l + 1] : st[l]) : val;
+            const float num = rv[l] + a * s;
+            v[l] = dv.safe ? fs_div(num, dv) : __fdiv_rn(num, c);
         }
-        // ring lanes take their nearest interior lane's value; fs_ring_value applies the x-face rule
-        if (first_x) v[0] = v[1];
-        if (last_x) v[3] = v[2];
+        if (fl & 0x01010101u) { // some lane is an obstacle cell (rare): copy / stale value instead
+            float st[4] = {cv[1], cv[2], cv[3], cv[4]};
+            if (MODE == FS_MODE_SMOOTH) {
+                const float4 s4 = ld4_plain(stale_src + idx);
+                st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
+            }
+#pragma unroll
+            for (int l = 0; l < 4; l++)
+                if ((fl >> (8 * l)) & 1u) v[l] = st[l];
+        }
 
         const int k = kl + g.zoff;
-        const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);       // extra ring row (y)
-        const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;          // ny == 3: both
         const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
-        const int kr2 = (HZ && k == 1 && k == g.nz - 2) ? kl + 1 : -1;      // nz == 3: both
-        const int zs[3] = {kl, kr, kr2}, fzs[3] = {0, 1, 1};
-        const int ys[3] = {j, jr, jr2}, fys[3] = {0, 1, 1};
+        if (xy_plain && kr < 0) { // interior thread, interior plane: one plain store
+            st4(out + idx, v);
+        } else {
+            // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
+            if (first_x) v[0] = v[1];
+            if (last_x) v[3] = v[2];
+            const int kr2 = (HZ && k == 1 && k == g.nz - 2) ? kl + 1 : -1; // nz == 3: both
+            const int zs[3] = {kl, kr, kr2}, fzs[3] = {0, 1, 1};
+            const int ys[3] = {j, jr, jr2}, fys[3] = {0, 1, 1};
 #pragma unroll
-        for (int zi = 0; zi < 3; zi++) {
-            if (zi > 0 && zs[zi] < 0) continue;
+            for (int zi = 0; zi < 3; zi++) {
+                if (zi > 0 && zs[zi] < 0) continue;
 #pragma unroll
-            for (int yi = 0; yi < 3; yi++) {
-                if (yi > 0 && ys[yi] < 0) continue;
-                float o[4];
+                for (int yi = 0; yi < 3; yi++) {
+                    if (yi > 0 && ys[yi] < 0) continue;
+                    float o[4];
 #pragma unroll
-                for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
-                st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+                    for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
+                    st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+                }
             }
         }
         prev = cur;

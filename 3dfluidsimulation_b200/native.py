@@ -30,7 +30,7 @@ EXPORTS = [
     "fs_op_set_bnd", "fs_op_diffuse", "fs_op_smooth", "fs_op_lin_solve", "fs_op_project", "fs_op_advect",
     "fs_op_advect_velocity", "fs_op_enforce_obstacles",
     "fs_timer_start", "fs_timer_stop", "fs_launch_count", "fs_bench_sweep",
-    "fs_halo_export", "fs_halo_connect",
+    "fs_selftest_division", "fs_halo_export", "fs_halo_connect",
 ]
 
 
@@ -94,6 +94,7 @@ def load(path: str | None = None) -> C.CDLL:
         "fs_timer_stop": (C.c_int, [vp, _F]),
         "fs_launch_count": (i64, [vp]),
         "fs_bench_sweep": (C.c_int, [vp, i32, i32, i32, _F, C.POINTER(C.c_double)]),
+        "fs_selftest_division": (C.c_int, [vp, f32, C.c_uint64, C.c_uint64, C.POINTER(C.c_uint64)]),
         "fs_halo_export": (C.c_int, [vp, vp, i64]),
         "fs_halo_connect": (C.c_int, [vp, vp, vp, i32]),
     }
@@ -250,6 +251,11 @@ class NativeSolver:
         ms, by = C.c_float(), C.c_double()
         self._ck(self.lib.fs_bench_sweep(self.h, kind, b, reps, C.byref(ms), C.byref(by)))
         return ms.value, by.value
+
+    def selftest_division(self, divisor, first_bits=0, count=1 << 32) -> int:
+        bad = C.c_uint64()
+        self._ck(self.lib.fs_selftest_division(self.h, divisor, first_bits, count, C.byref(bad)))
+        return int(bad.value)
 
     # -- multi-GPU wiring
     def halo_export(self) -> bytes:

@@ -145,6 +145,11 @@ int64_t fs_launch_count(const fs_solver *s);        /* kernels launched by this 
  * smoother, 1 = Jacobi, 2 = red-black full sweep) on scratch fields; fills the algorithmic bytes per launch. */
 int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes);
 
+/* Self-test of the sweep kernels' constant-divisor division (csrc/fs_kernels.cuh fs_div) against IEEE
+ * division, bit for bit, over numerator bit patterns [first_bits, first_bits + count).  Returns the
+ * number of mismatching quotients (0 expected). */
+int fs_selftest_division(fs_solver *s, float divisor, uint64_t first_bits, uint64_t count, uint64_t *mismatches);
+
 /* ---- multi-GPU wiring (z-slabs, one handle per GPU) ------------------- */
 #define FS_IPC_BLOB_BYTES 1024
 /* Export this handle's halo mailbox as an opaque blob (CUDA IPC handles inside). */

@@ -119,6 +119,7 @@ struct HostExec {
         *sum = acc;
         *mx = m;
     }
+    unsigned long long division_selftest(float, unsigned long long, unsigned long long) { return 0; } // plain `/` here
     void halo(const FsGrid &, float *) {}
     template <class Core> int halo_export(Core &, void *) { msg = "host emulation: no multi-GPU"; return FS_ERR_UNSUPPORTED; }
     template <class Core> int halo_connect(Core &, const void *, const void *, int) { msg = "host emulation: no multi-GPU"; return FS_ERR_UNSUPPORTED; }
