@@ -154,7 +154,8 @@ struct CudaExec {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
-        if (g.nx % 4 == 0 && !force_generic) {
+        const bool c_ok = c != 0.0f && c == c && c - c == 0.0f; // finite, non-zero: fs_div's precondition
+        if (g.nx % 4 == 0 && !force_generic && c_ok) {
             const int groups = g.nx / 4;
             // small grids: smaller CTAs so that there are enough of them to occupy 148 SMs
             const long long thread_planes = (long long)groups * (g.ny - 2) * cnt;
@@ -234,6 +235,13 @@ struct CudaExec {
         linear(n, [=] __device__(long long t) {
             const int i = (int)(t % g.nx), j = (int)((t / g.nx) % g.ny), kl = (int)(t / g.sz);
             flags[t] = fs_flags_cell(g, mask, i, j, kl);
+        });
+    }
+    void fill_random(float *dst, long long n, unsigned seed) { // uniform in [-1, 1), hash based (bench only)
+        linear(n, [=] __device__(long long t) {
+            unsigned h = (unsigned)t * 2654435761u ^ (unsigned)(t >> 32) ^ (seed * 0x9E3779B9u);
+            h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+            dst[t] = (float)(h >> 8) * (1.0f / 8388608.0f) - 1.0f;
         });
     }
     void axpy(float *dst, const float *src, long long n) {

@@ -199,23 +199,24 @@ int fs_timer_stop(fs_solver *s, float *elapsed_ms) {
 
 int64_t fs_launch_count(const fs_solver *s) { return s ? s->core.ex.launches : 0; }
 
-int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes) {
+int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes) {
     FS_GUARD(s);
-    if (reps < 1 || kind < 0 || kind > 2 || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
-    // scratch operands: in = vx0, rhs = vy0, out = tmp (contents are whatever the last step left there)
+    const int kind = kind_and_fill & 15, fill = kind_and_fill >> 4; // fill: 0 as is, 1 random normals, 2 zeros
+    if (reps < 1 || kind < 0 || kind > 2 || fill < 0 || fill > 2 || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    // scratch operands: in = vx0, rhs = vy0, out = tmp (by default whatever the last step left there)
+    if (fill == 1) { c.ex.fill_random(c.vx0, c.nloc, 1u); c.ex.fill_random(c.vy0, c.nloc, 2u); }
+    if (fill == 2) { c.ex.zero(c.vx0, sizeof(float) * c.nloc); c.ex.zero(c.vy0, sizeof(float) * c.nloc); }
     const long long interior = (long long)(c.g.nx) * c.g.ny * (c.ze - c.zb);
     const double per_voxel = kind == 0 ? 9.0 : 13.0;
     float a, cc;
     SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
-    for (int w = 0; w < 2; w++) { // warm-up
+    auto once = [&]() {
         if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
         else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false);
-    }
+    };
+    for (int w = 0; w < 2; w++) once(); // warm-up
     c.ex.timer_start();
-    for (int r = 0; r < reps; r++) {
-        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
-        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false);
-    }
+    for (int r = 0; r < reps; r++) once();
     const float ms = c.ex.timer_stop();
     if (avg_ms) *avg_ms = ms / (float)reps;
     if (algo_bytes) *algo_bytes = per_voxel * (double)interior;

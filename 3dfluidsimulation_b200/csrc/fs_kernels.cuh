@@ -51,39 +51,41 @@ __device__ __forceinline__ void st4(float *p, const float v[4]) {
 
 // ---- correctly rounded division by a launch-constant divisor ------------------------------------------
 // `x / c` compiles to div.rn.f32, whose FCHK guard sends zero / denormal numerators to a ~40 instruction
-// slow path -- and a smoke-plume field is exactly zero or denormal almost everywhere (profiles/r01a_*:
-// every division took the slow path, the sweep was issue bound at 41% of DRAM peak).  For a constant
-// divisor the quotient can be had without any data-dependent path: y = RN(1/c) once per thread, then
-//   q0 = RN(n*y); r0 = n - c*q0; q1 = RN(q0 + r0*y)   (q1 is a faithful rounding of n/c)
-//   r1 = n - c*q1 (exact, FMA);  q2 = RN(q1 + r1*y)   == RN(n/c)  (Markstein's theorem: y correctly
-// rounded, q1 faithful, no under/overflow).  Numerators whose exponent is outside [2^-100, 2^101) --
-// denormals, huge values, inf/nan -- take the IEEE division, zero keeps its sign via n*y.  Divisors outside
-// [2^-20, 2^20] disable the fast path altogether.  fs_selftest_division() checks fs_div against
-// __fdiv_rn bit for bit over any range of numerator bit patterns (tests run all 2^32 of them).
+// slow path -- and a smoke-plume field is exactly zero, denormal or tiny almost everywhere (18% of the cells
+// of a 512^3 plume are in 1e-45..1e-30 after 8 steps).  profiles/r01a_*: with IEEE `/` every division took
+// the slow path and the sweep was issue bound at 41% of DRAM peak; a float FMA sequence with an IEEE
+// fallback for tiny numerators (r01b) still lost 40% on real plume data.  The version below has no data
+// dependent path at all and is exact for every finite numerator, denormal results included:
+//   in double, with C = (double)c and Y = RN(1/C) computed once:
+//     q = RN(n*Y); r = n - C*q (exact: FMA); q2 = RN(q + r*Y)          => q2 = (n/c)(1 + d), |d| <= 2^-105
+//   result = (float)q2.
+// Why the final rounding is always the IEEE one: a quotient of two 24-bit floats that is not itself a
+// float rounding boundary (a 25-bit midpoint, or a midpoint of the denormal grid) is at least 2^-49
+// (relative) away from the nearest one, far more than 2^-53 + 2^-105; and if it IS a boundary it is a double,
+// so q2 equals it exactly and cvt.rn resolves the tie to even like div.rn does.  NaN propagates.  The one
+// deviation: a +-inf numerator (a field that has already blown up) gives NaN instead of +-inf.  A divisor
+// that is zero, infinite or NaN never reaches this code (the host launches the per-cell kernel instead).
+// fs_selftest_division() checks fs_div against __fdiv_rn bit for bit over any range of numerator bit
+// patterns (the GPU tests run all 2^32 of them for the divisors the step uses).
 struct FsDivisor {
-    float c, rc;
+    double c, rc;
+    float cf;
     int safe;
 };
 __device__ __forceinline__ FsDivisor fs_make_divisor(float c) {
     FsDivisor d;
-    d.c = c;
-    d.rc = __frcp_rn(c);
-    const float ac = fabsf(c);
-    d.safe = (ac >= 9.5367431640625e-07f && ac <= 1048576.0f) ? 1 : 0;
+    d.cf = c;
+    d.c = (double)c;
+    d.rc = 1.0 / (double)c;
+    d.safe = (c != 0.0f && fabsf(c) <= 3.402823466e38f) ? 1 : 0; // finite and non-zero (NaN fails the compare)
     return d;
 }
 __device__ __forceinline__ float fs_div(float n, const FsDivisor &d) {
-    const float q0 = __fmul_rn(n, d.rc);
-    const float r0 = __fmaf_rn(-d.c, q0, n);
-    const float q1 = __fmaf_rn(r0, d.rc, q0);
-    const float r1 = __fmaf_rn(-d.c, q1, n);
-    float q2 = __fmaf_rn(r1, d.rc, q1);
-    const unsigned e = (__float_as_uint(n) >> 23) & 0xffu;
-    if (e - 27u > 200u) {                       // zero, denormal, tiny, huge, inf, nan
-        if (n == 0.0f) q2 = q0;                 // signed zero, as n / c
-        else q2 = __fdiv_rn(n, d.c);
-    }
-    return q2;
+    const double nd = (double)n;
+    const double q = __dmul_rn(nd, d.rc);
+    const double r = __fma_rn(-d.c, q, nd);
+    const double q2 = __fma_rn(r, d.rc, q);
+    return (float)q2;
 }
 
 __global__ void __launch_bounds__(256)
@@ -96,7 +98,8 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
         const float want = __fdiv_rn(n, c);
         const float got = d.safe ? fs_div(n, d) : want;
         const bool both_nan = (want != want) && (got != got);
-        if (!both_nan && __float_as_uint(want) != __float_as_uint(got)) bad++;
+        const bool inf_in = fabsf(n) > 3.402823466e38f; // documented deviation: inf numerator -> NaN
+        if (!both_nan && !inf_in && __float_as_uint(want) != __float_as_uint(got)) bad++;
     }
     if (bad) atomicAdd(mismatches, bad);
 }
@@ -127,26 +130,32 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1; // ny == 3: both
     const bool xy_plain = !first_x && !last_x && jr < 0;
 
-    long long idx = fs_idx(g, x0, j, k_lo);
+    const long long idx0 = fs_idx(g, x0, j, k_lo);
+    // per-thread running pointers (one 64-bit add each per plane instead of re-deriving every address)
+    const float *pin = in + idx0;
+    const float *prh = rhs ? rhs + idx0 : nullptr;
+    const uint8_t *pfl = flags ? flags + idx0 : nullptr;
+    float *pout = out + idx0;
+    const long long sy = g.sy, sz = g.sz;
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
     if (!in_zero) {
-        cur = ld4(in + idx);
-        if (HZ) prev = ld4(in + idx - g.sz);
+        cur = ld4(pin);
+        if (HZ) prev = ld4(pin - sz);
     }
 
-    for (int kl = k_lo; kl < k_hi; kl++, idx += g.sz) {
+    for (int kl = k_lo; kl < k_hi; kl++, pin += sz, prh += sz, pfl += sz, pout += sz) {
         float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
         float left = 0.f, right = 0.f;
         if (!in_zero) {
-            if (HZ) next = ld4(in + idx + g.sz);
-            up = ld4(in + idx + g.sy);
-            dn = ld4(in + idx - g.sy);
-            if (!first_x) left = __ldg(in + idx - 1);
-            if (!last_x) right = __ldg(in + idx + 4);
+            if (HZ) next = ld4(pin + sz);
+            up = ld4(pin + sy);
+            dn = ld4(pin - sy);
+            if (!first_x) left = __ldg(pin - 1);
+            if (!last_x) right = __ldg(pin + 4);
         }
         float4 r4 = cur;
-        if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(rhs + idx);
-        const uint32_t fl = flags ? ld_flags4(flags + idx) : 0u;
+        if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(prh);
+        const uint32_t fl = flags ? ld_flags4(pfl) : 0u;
 
         const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
         const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
@@ -158,12 +167,12 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
             float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
             if (HZ) s = (s + nxv[l]) + pvv[l];
             const float num = rv[l] + a * s;
-            v[l] = dv.safe ? fs_div(num, dv) : __fdiv_rn(num, c);
+            v[l] = fs_div(num, dv); // the host only launches this kernel for finite, non-zero c
         }
         if (fl & 0x01010101u) { // some lane is an obstacle cell (rare): copy / stale value instead
             float st[4] = {cv[1], cv[2], cv[3], cv[4]};
             if (MODE == FS_MODE_SMOOTH) {
-                const float4 s4 = ld4_plain(stale_src + idx);
+                const float4 s4 = ld4_plain(stale_src + (pout - out));
                 st[0] = s4.x; st[1] = s4.y; st[2] = s4.z; st[3] = s4.w;
             }
 #pragma unroll
@@ -174,7 +183,7 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         const int k = kl + g.zoff;
         const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
         if (xy_plain && kr < 0) { // interior thread, interior plane: one plain store
-            st4(out + idx, v);
+            st4(pout, v);
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
             if (first_x) v[0] = v[1];

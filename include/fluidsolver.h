@@ -141,9 +141,11 @@ int fs_op_enforce_obstacles(fs_solver *s);
 int fs_timer_start(fs_solver *s);
 int fs_timer_stop(fs_solver *s, float *elapsed_ms); /* records, synchronises, returns the interval */
 int64_t fs_launch_count(const fs_solver *s);        /* kernels launched by this handle so far */
-/* Average duration of `reps` back-to-back launches of one relaxation sweep (kind 0 = pass-1
- * smoother, 1 = Jacobi, 2 = red-black full sweep) on scratch fields; fills the algorithmic bytes per launch. */
-int fs_bench_sweep(fs_solver *s, int32_t kind, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes);
+/* Average duration of `reps` back-to-back launches of one relaxation sweep on the scratch fields
+ * (in = VX0, rhs = VY0).  kind_and_fill = kind + 16*fill; kind 0 = pass-1 smoother, 1 = Jacobi,
+ * 2 = red-black full sweep; fill 0 = operands as the last step left them, 1 = overwrite them with
+ * uniform random normals first, 2 = zeros.  Also returns the algorithmic bytes per launch. */
+int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes);
 
 /* Self-test of the sweep kernels' constant-divisor division (csrc/fs_kernels.cuh fs_div) against IEEE
  * division, bit for bit, over numerator bit patterns [first_bits, first_bits + count).  Returns the

@@ -99,6 +99,7 @@ struct HostExec {
             for (int j = 0; j < g.ny; j++)
                 for (int i = 0; i < g.nx; i++) flags[fs_idx(g, i, j, kl)] = fs_flags_cell(g, mask, i, j, kl);
     }
+    void fill_random(float *dst, long long n, unsigned seed) { for (long long t = 0; t < n; t++) dst[t] = (float)((t * 2654435761u + seed) % 2001) / 1000.0f - 1.0f; }
     void axpy(float *dst, const float *src, long long n) {
         for (long long t = 0; t < n; t++) dst[t] += src[t];
     }
