@@ -83,8 +83,10 @@ __device__ __forceinline__ FsDivisor fs_make_divisor(float c) {
 __device__ __forceinline__ float fs_div(float n, const FsDivisor &d) {
     const double nd = (double)n;
     const double q = __dmul_rn(nd, d.rc);
-    const double r = __fma_rn(-d.c, q, nd);
-    const double q2 = __fma_rn(r, d.rc, q);
+    // residual as -(C*q - n) rather than (n - C*q): the same value, but for n = -0 it yields -0, so that the
+    // quotient keeps the sign IEEE division gives a zero numerator
+    const double t = __fma_rn(d.c, q, -nd);
+    const double q2 = __fma_rn(-t, d.rc, q);
     return (float)q2;
 }
 
