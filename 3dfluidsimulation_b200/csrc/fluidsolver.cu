@@ -8,6 +8,7 @@
 // There is no CPU path in this library: every operator launches a kernel on the handle's stream.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -86,6 +87,7 @@ struct CudaExec {
     }
     void close() {
         invalidate_graph();
+        halo_close();
         if (d_sum) cudaFree(d_sum);
         if (d_max) cudaFree(d_max);
         if (scratch) cudaFree(scratch);
@@ -113,7 +115,14 @@ struct CudaExec {
         FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         FS_CUDA(cudaStreamSynchronize(st));
     }
-    void sync() { FS_CUDA(cudaStreamSynchronize(st)); }
+    void sync() {
+        FS_CUDA(cudaStreamSynchronize(st));
+        if (halo_on && my_flags) {
+            unsigned e = 0;
+            FS_CUDA(cudaMemcpy(&e, my_flags + FS_HF_ERROR, sizeof(e), cudaMemcpyDeviceToHost));
+            if (e && !bad) { bad = true; msg = "advection back-trace left the neighbouring slab (slab too thin for this CFL)"; }
+        }
+    }
     void *get_scratch(size_t bytes) {
         if (bytes > scratch_bytes) {
             if (scratch) { cudaStreamSynchronize(st); cudaFree(scratch); }
@@ -136,6 +145,7 @@ struct CudaExec {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
+        flush_halo_wait();
         const dim3 block(64, 4, 1);
         const dim3 grid((g.nx - 2 + 63) / 64, (g.ny - 2 + 3) / 4, cnt);
         cells_kernel<<<grid, block, 0, st>>>(g, kl0, f);
@@ -144,13 +154,14 @@ struct CudaExec {
     template <class F>
     void linear(long long n, F f) {
         if (n <= 0) return;
+        flush_halo_wait();
         linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
         launches++;
     }
 
     // ---- sweeps ----------------------------------------------------------------------------------
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
-               const uint8_t *flags, float a, float c, int b, bool in_zero) {
+               const uint8_t *flags, float a, float c, int b, bool in_zero, bool fuse_halo) {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
@@ -175,12 +186,20 @@ struct CudaExec {
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
             const dim3 block(bx, by, 1), grid(gxn, gyn, nchunks);
             const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
-            if (mode == FS_MODE_SMOOTH) {
-                if (g.hz) relax_vec4<FS_MODE_SMOOTH, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
-                else relax_vec4<FS_MODE_SMOOTH, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+            FsHaloArgs h{};
+            if (halo_on && fuse_halo) { // the sweep itself waits for the neighbours, pushes its boundary planes and signals
+                const unsigned op = ++ops_since_commit;
+                h = halo_args(g, out, op);
+                pending_wait = op;
             } else {
-                if (g.hz) relax_vec4<FS_MODE_JACOBI, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
-                else relax_vec4<FS_MODE_JACOBI, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc);
+                flush_halo_wait();
+            }
+            if (mode == FS_MODE_SMOOTH) {
+                if (g.hz) relax_vec4<FS_MODE_SMOOTH, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h);
+                else relax_vec4<FS_MODE_SMOOTH, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h);
+            } else {
+                if (g.hz) relax_vec4<FS_MODE_JACOBI, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h);
+                else relax_vec4<FS_MODE_JACOBI, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h);
             }
             launches++;
             return;
@@ -189,6 +208,7 @@ struct CudaExec {
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         else
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+        if (fuse_halo) halo(g, out); // per-cell fallback has no fused exchange
     }
     void rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour) {
         cells(g, [=] __device__(int i, int j, int kl) {
@@ -211,19 +231,32 @@ struct CudaExec {
     void gradient(const FsGrid &g, float *ux, float *uy, float *uz, const float *p, const uint8_t *flags) {
         cells(g, [=] __device__(int i, int j, int kl) { fs_gradient_cell(g, ux, uy, uz, p, flags, i, j, kl); });
     }
+    FsSlabView slab_view(const FsGrid &g, const float *field) const {
+        FsSlabView v{};
+        v.loc = field; v.zoff = g.zoff; v.nzl = g.nzl;
+        if (halo_on) {
+            const int bi = buf_index(field);
+            if (lo.present && bi >= 0) { v.lo = lo.base[bi]; v.lo_zoff = lo.zoff; v.lo_nzl = lo.nzl; }
+            if (hi.present && bi >= 0) { v.hi = hi.base[bi]; v.hi_zoff = hi.zoff; v.hi_nzl = hi.nzl; }
+            v.err = my_flags + FS_HF_ERROR;
+        }
+        return v;
+    }
     void advect(const FsGrid &g, float *d, const float *d0, const float *ux, const float *uy, const float *uz,
                 const uint8_t *flags, float dt0, int b) {
+        const FsSlabView v = slab_view(g, d0);
         cells(g, [=] __device__(int i, int j, int kl) {
-            auto samp = [&](int ii, int jj, int kk) { return __ldg(d0 + fs_idx(g, ii, jj, kk - g.zoff)); };
+            auto samp = [&](int ii, int jj, int kk) { return fs_slab_fetch(v, g, ii, jj, kk); };
             fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
         });
     }
     void advect_velocity(const FsGrid &g, float *dx, float *dy, float *dz, const float *sx, const float *sy,
                          const float *sz, const uint8_t *flags, float dt0) {
+        const FsSlabView vx_ = slab_view(g, sx), vy_ = slab_view(g, sy), vz_ = g.hz ? slab_view(g, sz) : FsSlabView{};
         cells(g, [=] __device__(int i, int j, int kl) {
-            auto px = [&](int ii, int jj, int kk) { return __ldg(sx + fs_idx(g, ii, jj, kk - g.zoff)); };
-            auto py = [&](int ii, int jj, int kk) { return __ldg(sy + fs_idx(g, ii, jj, kk - g.zoff)); };
-            auto pz = [&](int ii, int jj, int kk) { return __ldg(sz + fs_idx(g, ii, jj, kk - g.zoff)); };
+            auto px = [&](int ii, int jj, int kk) { return fs_slab_fetch(vx_, g, ii, jj, kk); };
+            auto py = [&](int ii, int jj, int kk) { return fs_slab_fetch(vy_, g, ii, jj, kk); };
+            auto pz = [&](int ii, int jj, int kk) { return fs_slab_fetch(vz_, g, ii, jj, kk); };
             fs_advect_velocity_cell(g, dx, dy, dz, px, py, pz, sx, sy, sz, flags, dt0, i, j, kl);
         });
     }
@@ -298,9 +331,164 @@ struct CudaExec {
     }
 
     // ---- halo exchange (z-slabs) ---------------------------------------------------------------------
-    void halo(const FsGrid &, float *) {} // single slab: nothing to exchange (multi-GPU: DESIGN.md section 6)
-    template <class Core> int halo_export(Core &, void *) { msg = "multi-GPU halo exchange not available in this build"; return FS_ERR_UNSUPPORTED; }
-    template <class Core> int halo_connect(Core &, const void *, const void *, int) { msg = "multi-GPU halo exchange not available in this build"; return FS_ERR_UNSUPPORTED; }
+    // See fs_kernels.cuh ("z-slab halo exchange over peer memory") for the protocol.
+    struct HaloBlob {              // what fs_halo_export hands to the neighbours (<= FS_IPC_BLOB_BYTES)
+        uint32_t magic;
+        int32_t rank, world, dev, nzl, kb, ke, zoff, nbuf;
+        uint64_t pid;
+        cudaIpcMemHandle_t field[11];
+        cudaIpcMemHandle_t flags;
+        void *raw_field[11];
+        void *raw_flags;
+    };
+    struct Peer {
+        bool present = false, ipc = false;
+        float *base[11] = {};
+        unsigned *flags = nullptr;
+        int nzl = 0, kb = 0, ke = 0, zoff = 0, dev = -1;
+    };
+    bool halo_on = false;
+    Peer lo, hi;
+    unsigned *my_flags = nullptr;       // FS_HF_WORDS words, device
+    std::vector<float *> bufs;          // this slab's field allocations, same order on every rank
+    unsigned ops_since_commit = 0;      // halo ops enqueued since the last halo_commit
+    unsigned pending_wait = 0;          // op offset whose completion by the neighbours nobody has waited for yet
+
+    int buf_index(const float *p) const {
+        for (size_t i = 0; i < bufs.size(); i++)
+            if (bufs[i] == p) return (int)i;
+        return -1;
+    }
+    FsHaloArgs halo_args(const FsGrid &g, const float *field, unsigned op_offset) const {
+        FsHaloArgs h{};
+        h.enabled = halo_on ? 1 : 0;
+        if (!halo_on) return h;
+        const int bi = field ? buf_index(field) : -1;
+        h.my_flags = my_flags;
+        h.op_offset = op_offset;
+        if (lo.present) {
+            h.lo_flags = lo.flags;
+            if (bi >= 0) h.lo_plane = lo.base[bi] + g.sz * (lo.nzl - 1);
+        }
+        if (hi.present) {
+            h.hi_flags = hi.flags;
+            if (bi >= 0) h.hi_plane = hi.base[bi];
+        }
+        return h;
+    }
+    // Consumers without a fused wait (every kernel except relax_vec4) must see the neighbours' last op.
+    void flush_halo_wait() {
+        if (!halo_on || !pending_wait) return;
+        halo_wait_kernel<<<1, 1, 0, st>>>(halo_args(FsGrid{}, nullptr, pending_wait));
+        launches++;
+        pending_wait = 0;
+    }
+    void halo(const FsGrid &g, float *field) {
+        if (!halo_on) return;
+        const unsigned op = ++ops_since_commit;
+        const FsHaloArgs h = halo_args(g, field, op);
+        const float *lo_src = field ? field + g.sz * g.kb : nullptr, *hi_src = field ? field + g.sz * (g.ke - 1) : nullptr;
+        const long long plane = g.sz;
+        int blocks = (int)((plane / 4 + 255) / 256);
+        if (blocks > sm_count * 2) blocks = sm_count * 2;
+        if (blocks < 1 || !field) blocks = 1;
+        halo_push_kernel<<<blocks, 256, 0, st>>>(h, lo_src, hi_src, field ? plane : 0);
+        launches++;
+        pending_wait = op;
+    }
+    void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
+        if (!halo_on) return;
+        halo(FsGrid{}, nullptr);
+        flush_halo_wait();
+    }
+    void halo_commit() {
+        if (!halo_on || !ops_since_commit) return;
+        flush_halo_wait();
+        halo_commit_kernel<<<1, 1, 0, st>>>(my_flags, ops_since_commit);
+        launches++;
+        ops_since_commit = 0;
+    }
+    template <class Core>
+    int halo_export(Core &c, void *blob) {
+        static_assert(sizeof(HaloBlob) <= FS_IPC_BLOB_BYTES, "blob too large");
+        if (c.prm.slab_count < 2) { msg = "halo export needs slab_count >= 2"; return FS_ERR_BAD_ARGUMENT; }
+        if (!my_flags) {
+            my_flags = (unsigned *)alloc(sizeof(unsigned) * FS_HF_WORDS);
+            if (!my_flags) return FS_ERR_OUT_OF_MEMORY;
+            FS_CUDA(cudaMemset(my_flags, 0, sizeof(unsigned) * FS_HF_WORDS));
+        }
+        bufs = c.allocated;
+        HaloBlob b{};
+        b.magic = 0x46534831u;
+        b.rank = c.prm.slab_rank; b.world = c.prm.slab_count; b.dev = dev;
+        b.nzl = c.g.nzl; b.kb = c.g.kb; b.ke = c.g.ke; b.zoff = c.g.zoff; b.nbuf = (int)bufs.size();
+        b.pid = (uint64_t)getpid();
+        for (size_t i = 0; i < bufs.size(); i++) {
+            FS_CUDA(cudaIpcGetMemHandle(&b.field[i], bufs[i]));
+            b.raw_field[i] = bufs[i];
+        }
+        FS_CUDA(cudaIpcGetMemHandle(&b.flags, my_flags));
+        b.raw_flags = my_flags;
+        memcpy(blob, &b, sizeof(b));
+        return bad ? FS_ERR_CUDA : FS_OK;
+    }
+    int connect_one(Peer &p, const void *blob, int expect_rank, int same_process) {
+        HaloBlob b;
+        memcpy(&b, blob, sizeof(b));
+        if (b.magic != 0x46534831u || b.rank != expect_rank || b.nbuf != (int)bufs.size()) { msg = "halo blob does not match the expected neighbour"; return FS_ERR_BAD_ARGUMENT; }
+        p.nzl = b.nzl; p.kb = b.kb; p.ke = b.ke; p.zoff = b.zoff; p.dev = b.dev;
+        if (same_process) {
+            if (b.dev != dev) {
+                int can = 0;
+                FS_CUDA(cudaDeviceCanAccessPeer(&can, dev, b.dev));
+                if (!can) { msg = "no peer access between the two devices"; return FS_ERR_COMM; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(b.dev, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess", e); return FS_ERR_COMM; }
+                cudaGetLastError();
+            }
+            for (int i = 0; i < b.nbuf; i++) p.base[i] = (float *)b.raw_field[i];
+            p.flags = (unsigned *)b.raw_flags;
+        } else {
+            for (int i = 0; i < b.nbuf; i++) {
+                void *ptr = nullptr;
+                cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.field[i], cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(field)", e); return FS_ERR_COMM; }
+                p.base[i] = (float *)ptr;
+            }
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, b.flags, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) { set_error("cudaIpcOpenMemHandle(flags)", e); return FS_ERR_COMM; }
+            p.flags = (unsigned *)ptr;
+            p.ipc = true;
+        }
+        p.present = true;
+        return FS_OK;
+    }
+    template <class Core>
+    int halo_connect(Core &c, const void *lower_blob, const void *upper_blob, int same_process) {
+        if (!my_flags) { msg = "call fs_halo_export first"; return FS_ERR_BAD_ARGUMENT; }
+        const int r = c.prm.slab_rank, P = c.prm.slab_count;
+        if ((r > 0) != (lower_blob != nullptr) || (r < P - 1) != (upper_blob != nullptr)) { msg = "a blob is needed for exactly the existing neighbours"; return FS_ERR_BAD_ARGUMENT; }
+        int rc = FS_OK;
+        if (lower_blob) rc = connect_one(lo, lower_blob, r - 1, same_process);
+        if (rc == FS_OK && upper_blob) rc = connect_one(hi, upper_blob, r + 1, same_process);
+        if (rc != FS_OK) return rc;
+        halo_on = true;
+        invalidate_graph();
+        return FS_OK;
+    }
+    void halo_close() {
+        for (Peer *p : {&lo, &hi}) {
+            if (p->present && p->ipc) {
+                for (float *b : p->base) if (b) cudaIpcCloseMemHandle(b);
+                if (p->flags) cudaIpcCloseMemHandle(p->flags);
+            }
+            *p = Peer{};
+        }
+        if (my_flags) cudaFree(my_flags);
+        my_flags = nullptr;
+        halo_on = false;
+    }
 
     // ---- CUDA graph capture / replay of one step --------------------------------------------------------
     void invalidate_graph() {

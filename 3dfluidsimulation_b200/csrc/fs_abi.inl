@@ -157,7 +157,9 @@ int fs_op_advect(fs_solver *s, int32_t dst, int32_t src, int32_t b, int32_t use_
     float *ux = use_v0_fields ? c.vx0 : c.vx, *uy = use_v0_fields ? c.vy0 : c.vy, *uz = use_v0_fields ? c.vz0 : c.vz;
     if (d == ux || d == uy || d == uz) return c.fail(FS_ERR_BAD_ARGUMENT, "dst aliases the carrier velocity");
     const float dt0 = dt * (float)(c.g.nx - 2);
+    c.ex.halo_fence();
     c.ex.advect(c.g, d, d0, ux, uy, uz, c.fl(), dt0, b);
+    if (b == 3 && c.n_obst) c.ex.halo(c.g, d);
     c.mirror(d, b);
     c.ex.halo(c.g, d);
     return c.check();
@@ -166,7 +168,9 @@ int fs_op_advect(fs_solver *s, int32_t dst, int32_t src, int32_t b, int32_t use_
 int fs_op_advect_velocity(fs_solver *s, float dt) {
     FS_GUARD(s);
     const float dt0 = dt * (float)(c.g.nx - 2);
+    c.ex.halo_fence();
     c.ex.advect_velocity(c.g, c.vx, c.vy, c.vz, c.vx0, c.vy0, c.vz0, c.fl(), dt0);
+    if (c.g.hz && c.n_obst) c.ex.halo(c.g, c.vz);
     c.mirror(c.vx, 1);
     c.mirror(c.vy, 2);
     if (c.g.hz) c.mirror(c.vz, 3);
@@ -212,7 +216,7 @@ int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps,
     SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
     auto once = [&]() {
         if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
-        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false);
+        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false, true);
     };
     for (int w = 0; w < 2; w++) once(); // warm-up
     c.ex.timer_start();

@@ -93,6 +93,7 @@ struct SolverCore {
 
     int fail(int code, const std::string &m) { err = m; return code; }
     int check() {
+        ex.halo_commit();
         if (ex.failed()) return fail(FS_ERR_CUDA, ex.error());
         return FS_OK;
     }
@@ -176,6 +177,20 @@ struct SolverCore {
     void mirror(float *x, int b) {
         if (b != 0 && n_obst && (b != 3 || g.hz)) ex.mirror(g, x, flags, obst_list, n_obst, b);
     }
+    // One relaxation sweep + its boundary work.  Single slab: sweep, obstacle mirroring.  Several slabs: the
+    // sweep pushes its boundary planes into the neighbours' ghosts itself (fused halo) unless obstacle
+    // mirroring has to run on the boundary planes first (b != 0 with obstacles): then the order is
+    // sweep, [halo when the mirror reads z neighbours], mirror, halo.
+    void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,
+                  bool in_zero) {
+        const bool mir = b != 0 && n_obst && (b != 3 || g.hz);
+        ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/!mir);
+        if (mir) {
+            if (b == 3) ex.halo(g, out);
+            mirror(out, b);
+            ex.halo(g, out);
+        }
+    }
     // pass 1, DiffuseWithJobs :1292-1357.  Result ends in `x` (roles of x and tmp may swap).
     void smooth(int b, float *&x, const float *x0, float a, float c, int iters) {
         if (iters == 0) { ex.copy(x, x0, sizeof(float) * nloc); return; }
@@ -183,9 +198,7 @@ struct SolverCore {
         const float *in = x0;
         for (int it = 0; it < iters; it++) {
             float *out = (it & 1) ? B : A;
-            ex.relax(FS_MODE_SMOOTH, g, in, nullptr, it < 2 ? x0 : nullptr, out, fl(), a, c, b, false);
-            mirror(out, b);
-            ex.halo(g, out);
+            relax_op(FS_MODE_SMOOTH, in, nullptr, it < 2 ? x0 : nullptr, out, a, c, b, false);
             in = out;
         }
         float *res = const_cast<float *>(in);
@@ -197,9 +210,7 @@ struct SolverCore {
         if (iters == 0) { if (zero_guess) ex.zero(x, sizeof(float) * nloc); return; }
         float *rd = x, *wr = tmp;
         for (int it = 0; it < iters; it++) {
-            ex.relax(FS_MODE_JACOBI, g, rd, rhs, nullptr, wr, fl(), a, c, b, zero_guess && it == 0);
-            mirror(wr, b);
-            ex.halo(g, wr);
+            relax_op(FS_MODE_JACOBI, rd, rhs, nullptr, wr, a, c, b, zero_guess && it == 0);
             std::swap(rd, wr);
         }
         x = rd;
@@ -232,6 +243,7 @@ struct SolverCore {
         else
             lin_solve(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true); // :1581-1582, p starts 0
         ex.gradient(g, ux, uy, uz, pressure, fl());
+        if (g.hz && n_obst) ex.halo(g, uz); // slabs: the z mirror reads the neighbours' new boundary planes
         mirror(ux, 1);
         mirror(uy, 2);
         if (g.hz) mirror(uz, 3);
@@ -248,7 +260,9 @@ struct SolverCore {
         diffuse(2, vy0, vy, visc, dt);
         if (g.hz) diffuse(3, vz0, vz, visc, dt);
         project(vx0, vy0, vz0);
+        ex.halo_fence(); // slabs: the back-trace may gather from a neighbour slab, whose fields must be complete
         ex.advect_velocity(g, vx, vy, vz, vx0, vy0, vz0, fl(), dt0); // :710-711
+        if (g.hz && n_obst) ex.halo(g, vz);
         mirror(vx, 1);
         mirror(vy, 2);
         if (g.hz) mirror(vz, 3);
@@ -258,6 +272,7 @@ struct SolverCore {
         project(vx, vy, vz);
         // DensityStep :716-721
         diffuse(0, dens0, density, diff, dt);
+        ex.halo_fence();
         ex.advect(g, density, dens0, vx, vy, vz, fl(), dt0, 0);
         ex.halo(g, density);
         if (prm.enable_obstacle && any_obstacle) { // :567-570
@@ -266,6 +281,7 @@ struct SolverCore {
             ex.halo(g, vy);
             if (g.hz) ex.halo(g, vz);
         }
+        ex.halo_commit();
     }
 
     int step(float dt, float visc, float diff) {

@@ -106,6 +106,112 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
     if (bad) atomicAdd(mismatches, bad);
 }
 
+// ---- z-slab halo exchange over peer memory (NVLink P2P) ----------------------------------------------
+// One process (or handle) per GPU.  A slab's neighbours map its field buffers and its flag block (CUDA IPC
+// or plain peer access) and STORE boundary planes straight into its ghost planes; there is no receive
+// side copy and no collective.  Every halo-producing operation has a sequence number
+//     seq = flags[FS_HF_BASE] + op_offset
+// (FS_HF_BASE lives in device memory and is advanced by halo_commit_kernel, so a CUDA graph replays with
+// fresh numbers).  Protocol of operation `seq` on every rank ("strict lock step"):
+//   wait   flags[FROM_LO] >= seq-1 and flags[FROM_HI] >= seq-1   (neighbours finished op seq-1: their
+//          stores into my ghosts have landed AND they no longer read the ghosts I am about to overwrite)
+//   store  my lowest owned plane -> lower neighbour's top ghost plane, my highest -> upper's plane 0
+//   signal __threadfence_system(); neighbour.flags[FROM_HI or FROM_LO] = seq
+// In relax_vec4 the three steps are done by the CTAs that own the boundary planes (first / last z chunk)
+// while every other CTA streams the interior -- the exchange overlaps the sweep tile by tile.
+enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_CNT_HI = 4, FS_HF_ERROR = 5, FS_HF_WORDS = 8 };
+
+struct FsHaloArgs {
+    float *lo_plane;        // lower neighbour's top ghost plane of the output field (nullptr: no neighbour)
+    float *hi_plane;        // upper neighbour's plane 0 of the output field
+    unsigned *my_flags;     // this slab's flag block
+    unsigned *lo_flags;     // neighbours' flag blocks (peer memory)
+    unsigned *hi_flags;
+    unsigned op_offset;
+    int enabled;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void halo_spin_until(const unsigned *flag, unsigned target) {
+    while ((int)(ld_acquire_sys(flag) - target) < 0) __nanosleep(64);
+}
+__device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
+    return *(volatile const unsigned *)(h.my_flags + FS_HF_BASE) + h.op_offset;
+}
+
+// Standalone form for the once-per-step kernels: copies the two boundary planes of `field` (nullptr: pure
+// fence) after waiting for seq-1, then signals seq.  plane_elems = nx*ny.
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const float *__restrict__ hi_src, long long plane_elems) {
+    __shared__ unsigned s_seq;
+    if (threadIdx.x == 0) {
+        const unsigned seq = halo_seq(h);
+        if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
+        if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
+        s_seq = seq;
+    }
+    __syncthreads();
+    const long long n4 = plane_elems / 4, stride = (long long)gridDim.x * blockDim.x;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+        if (h.lo_plane && lo_src) reinterpret_cast<float4 *>(h.lo_plane)[t] = reinterpret_cast<const float4 *>(lo_src)[t];
+        if (h.hi_plane && hi_src) reinterpret_cast<float4 *>(h.hi_plane)[t] = reinterpret_cast<const float4 *>(hi_src)[t];
+    }
+    for (long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane_elems; t += stride) {
+        if (h.lo_plane && lo_src) h.lo_plane[t] = lo_src[t];
+        if (h.hi_plane && hi_src) h.hi_plane[t] = hi_src[t];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == gridDim.x - 1) {
+            h.my_flags[FS_HF_CNT_LO] = 0;
+            __threadfence_system();
+            if (h.lo_flags) st_release_sys(h.lo_flags + FS_HF_FROM_HI, s_seq);
+            if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
+        }
+    }
+}
+
+// Consumer side for kernels without a fused wait: returns when both neighbours have completed op seq.
+__global__ void halo_wait_kernel(const FsHaloArgs h) {
+    const unsigned seq = halo_seq(h);
+    if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq);
+    if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq);
+}
+
+__global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
+
+// Gather source for the semi-Lagrangian back-trace: a field as seen from one slab -- its own planes
+// (ghosts included) plus the two neighbour slabs' copies through peer memory (NVLink loads).  A back-trace
+// that leaves even the neighbour slabs sets FS_HF_ERROR (reported by fs_sync / fs_get_field).
+struct FsSlabView {
+    const float *loc, *lo, *hi;
+    int zoff, nzl, lo_zoff, lo_nzl, hi_zoff, hi_nzl;
+    unsigned *err;
+};
+__device__ __forceinline__ float fs_slab_fetch(const FsSlabView &v, const FsGrid &g, int ii, int jj, int kk) {
+    int kl = kk - v.zoff;
+    const float *base = v.loc;
+    if (kl < 0) {
+        base = v.lo; kl = kk - v.lo_zoff;
+        if (!base || kl < 0) { if (v.err) *v.err = 1u; return 0.0f; }
+        return base[ii + jj * g.sy + kl * g.sz];
+    }
+    if (kl >= v.nzl) {
+        base = v.hi; kl = kk - v.hi_zoff;
+        if (!base || kl >= v.hi_nzl) { if (v.err) *v.err = 1u; return 0.0f; }
+        return base[ii + jj * g.sy + kl * g.sz];
+    }
+    return __ldg(base + ii + jj * g.sy + kl * g.sz);
+}
+
 // ---- the hot sweep ---------------------------------------------------------------------------------
 // Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
@@ -114,15 +220,33 @@ template <int MODE, bool HZ>
 __global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
-           const int in_zero, const int kl_begin, const int kl_end, const int zchunk) {
+           const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const FsHaloArgs h) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int x0 = gx * 4;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    if (x0 >= g.nx || j > g.ny - 2) return;
-    const int k_lo = kl_begin + blockIdx.z * zchunk;
+    // z chunk of this CTA.  CTAs are dispatched in blockIdx order (z slowest), so the two chunks that hold
+    // the slab's boundary planes are mapped to blockIdx.z = 0 and 1: their halo stores and flags go out at
+    // the START of the sweep and the neighbours' next sweep finds them long before it needs them.
+    const int nzc = gridDim.z;
+    const int zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1);
+    const int k_lo = kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
-    if (k_lo >= k_hi) return;
+    const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
 
+    // fused halo exchange: CTAs of the first / last z chunk talk to the lower / upper neighbour slab
+    const bool link_lo = h.enabled && h.lo_flags && zc == 0;
+    const bool link_hi = h.enabled && h.hi_flags && zc == nzc - 1;
+    const int kl_push_lo = link_lo ? kl_begin : -1, kl_push_hi = link_hi ? kl_end - 1 : -1;
+    unsigned seq = 0;
+    if (link_lo || link_hi) {
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            seq = halo_seq(h);
+            if (link_lo) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
+            if (link_hi) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
+        }
+        __syncthreads();
+    }
+    if (active) {
     const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
     const int fxl[4] = {first_x ? 1 : 0, 0, 0, last_x ? 1 : 0};
@@ -184,7 +308,7 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 
         const int k = kl + g.zoff;
         const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
-        if (xy_plain && kr < 0) { // interior thread, interior plane: one plain store
+        if (xy_plain && kr < 0 && kl != kl_push_lo && kl != kl_push_hi) { // interior thread, interior plane
             st4(pout, v);
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
@@ -203,11 +327,33 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 #pragma unroll
                     for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
                     st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+                    if (zi == 0) { // boundary plane of the slab: the same row goes into the neighbour's ghost plane
+                        if (kl == kl_push_lo) st4(h.lo_plane + x0 + ys[yi] * sy, o);
+                        if (kl == kl_push_hi) st4(h.hi_plane + x0 + ys[yi] * sy, o);
+                    }
                 }
             }
         }
         prev = cur;
         cur = next;
+    }
+    } // active
+    if (link_lo || link_hi) {
+        __syncthreads(); // every thread of the CTA has issued its peer stores
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            __threadfence_system();
+            const unsigned ctas = gridDim.x * gridDim.y;
+            if (link_lo && atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ctas - 1) {
+                h.my_flags[FS_HF_CNT_LO] = 0;
+                __threadfence_system();
+                st_release_sys(h.lo_flags + FS_HF_FROM_HI, seq);
+            }
+            if (link_hi && atomicAdd(h.my_flags + FS_HF_CNT_HI, 1u) == ctas - 1) {
+                h.my_flags[FS_HF_CNT_HI] = 0;
+                __threadfence_system();
+                st_release_sys(h.hi_flags + FS_HF_FROM_LO, seq);
+            }
+        }
     }
 }
 

@@ -10,7 +10,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <chrono>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -51,11 +53,12 @@ struct HostExec {
     }
 
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
-               const uint8_t *flags, float a, float c, int b, bool in_zero) {
+               const uint8_t *flags, float a, float c, int b, bool in_zero, bool fuse_halo) {
         if (mode == FS_MODE_SMOOTH)
             cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         else
             cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+        if (fuse_halo) halo(g, out);
     }
     void rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour) {
         cells(g, [&](int i, int j, int kl) {
@@ -78,16 +81,16 @@ struct HostExec {
     void advect(const FsGrid &g, float *d, const float *d0, const float *ux, const float *uy, const float *uz,
                 const uint8_t *flags, float dt0, int b) {
         cells(g, [&](int i, int j, int kl) {
-            auto samp = [&](int ii, int jj, int kk) { return d0[fs_idx(g, ii, jj, kk - g.zoff)]; };
+            auto samp = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, d0, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
             fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
         });
     }
     void advect_velocity(const FsGrid &g, float *dx, float *dy, float *dz, const float *sx, const float *sy,
                          const float *sz, const uint8_t *flags, float dt0) {
         cells(g, [&](int i, int j, int kl) {
-            auto px = [&](int ii, int jj, int kk) { return sx[fs_idx(g, ii, jj, kk - g.zoff)]; };
-            auto py = [&](int ii, int jj, int kk) { return sy[fs_idx(g, ii, jj, kk - g.zoff)]; };
-            auto pz = [&](int ii, int jj, int kk) { return sz[fs_idx(g, ii, jj, kk - g.zoff)]; };
+            auto px = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sx, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
+            auto py = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sy, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
+            auto pz = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sz, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
             fs_advect_velocity_cell(g, dx, dy, dz, px, py, pz, sx, sy, sz, flags, dt0, i, j, kl);
         });
     }
@@ -121,9 +124,87 @@ struct HostExec {
         *mx = m;
     }
     unsigned long long division_selftest(float, unsigned long long, unsigned long long) { return 0; } // plain `/` here
-    void halo(const FsGrid &, float *) {}
-    template <class Core> int halo_export(Core &, void *) { msg = "host emulation: no multi-GPU"; return FS_ERR_UNSUPPORTED; }
-    template <class Core> int halo_connect(Core &, const void *, const void *, int) { msg = "host emulation: no multi-GPU"; return FS_ERR_UNSUPPORTED; }
+    // ---- multi-slab emulation: one host thread per slab handle, same lock-step protocol as the CUDA
+    // executor (wait for the neighbours' op seq-1, store boundary planes into their ghosts, publish seq,
+    // wait for the neighbours' seq) with std::atomic instead of device flags.
+    struct HostBlob {
+        uint32_t magic;
+        int32_t rank, nzl, kb, ke, zoff, nbuf;
+        void *raw_field[11];
+        std::atomic<unsigned> *seq;
+    };
+    struct Peer {
+        bool present = false;
+        float *base[11] = {};
+        std::atomic<unsigned> *seq = nullptr;
+        int nzl = 0, zoff = 0;
+    };
+    bool halo_on = false;
+    Peer lo, hi;
+    std::atomic<unsigned> *my_seq = nullptr;
+    unsigned ops = 0;
+    std::vector<float *> bufs;
+    int buf_index(const float *p) const {
+        for (size_t i = 0; i < bufs.size(); i++)
+            if (bufs[i] == p) return (int)i;
+        return -1;
+    }
+    static void spin(std::atomic<unsigned> *a, unsigned target) {
+        while ((int)(a->load(std::memory_order_acquire) - target) < 0) std::this_thread::yield();
+    }
+    void halo(const FsGrid &g, float *field) {
+        if (!halo_on) return;
+        const unsigned op = ++ops;
+        if (lo.present) spin(lo.seq, op - 1);
+        if (hi.present) spin(hi.seq, op - 1);
+        const int bi = field ? buf_index(field) : -1;
+        if (bi >= 0) {
+            if (lo.present) memcpy(lo.base[bi] + g.sz * (lo.nzl - 1), field + g.sz * g.kb, sizeof(float) * g.sz);
+            if (hi.present) memcpy(hi.base[bi], field + g.sz * (g.ke - 1), sizeof(float) * g.sz);
+        }
+        my_seq->store(op, std::memory_order_release);
+        if (lo.present) spin(lo.seq, op);
+        if (hi.present) spin(hi.seq, op);
+    }
+    void halo_fence() { halo(FsGrid{}, nullptr); }
+    void halo_commit() {}
+    template <class Core> int halo_export(Core &c, void *blob) {
+        if (!my_seq) my_seq = new std::atomic<unsigned>(0);
+        bufs = c.allocated;
+        HostBlob b{};
+        b.magic = 0x48454d31u; b.rank = c.prm.slab_rank; b.nzl = c.g.nzl; b.kb = c.g.kb; b.ke = c.g.ke; b.zoff = c.g.zoff;
+        b.nbuf = (int)bufs.size();
+        for (size_t i = 0; i < bufs.size(); i++) b.raw_field[i] = bufs[i];
+        b.seq = my_seq;
+        static_assert(sizeof(HostBlob) <= FS_IPC_BLOB_BYTES, "blob too large");
+        memcpy(blob, &b, sizeof(b));
+        return FS_OK;
+    }
+    int connect_one(Peer &p, const void *blob, int expect_rank) {
+        HostBlob b;
+        memcpy(&b, blob, sizeof(b));
+        if (b.magic != 0x48454d31u || b.rank != expect_rank) { msg = "blob mismatch"; return FS_ERR_BAD_ARGUMENT; }
+        for (int i = 0; i < b.nbuf; i++) p.base[i] = (float *)b.raw_field[i];
+        p.seq = b.seq; p.nzl = b.nzl; p.zoff = b.zoff; p.present = true;
+        return FS_OK;
+    }
+    template <class Core> int halo_connect(Core &c, const void *lower_blob, const void *upper_blob, int same_process) {
+        if (!same_process || !my_seq) { msg = "host emulation: same_process only, export first"; return FS_ERR_UNSUPPORTED; }
+        int rc = FS_OK;
+        if (lower_blob) rc = connect_one(lo, lower_blob, c.prm.slab_rank - 1);
+        if (rc == FS_OK && upper_blob) rc = connect_one(hi, upper_blob, c.prm.slab_rank + 1);
+        halo_on = rc == FS_OK;
+        return rc;
+    }
+    const float *resolve(const FsGrid &g, const float *field, int kk, int *kl) const { // slab view for advect
+        int l = kk - g.zoff;
+        if (l >= 0 && l < g.nzl) { *kl = l; return field; }
+        const int bi = buf_index(field);
+        if (l < 0 && lo.present) { *kl = kk - lo.zoff; return lo.base[bi]; }
+        if (l >= g.nzl && hi.present) { *kl = kk - hi.zoff; return hi.base[bi]; }
+        *kl = 0;
+        return nullptr;
+    }
     void invalidate_graph() {}
     bool replay_step(float, float, float, float *const[11]) { return false; }
     void roles_after_replay(float **[11]) {}
