@@ -236,11 +236,9 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     // fused halo exchange: CTAs of the first / last z chunk talk to the lower / upper neighbour slab
     const bool link_lo = h.enabled && h.lo_flags && zc == 0;
     const bool link_hi = h.enabled && h.hi_flags && zc == nzc - 1;
-    const int kl_push_lo = link_lo ? kl_begin : -1, kl_push_hi = link_hi ? kl_end - 1 : -1;
-    unsigned seq = 0;
     if (link_lo || link_hi) {
         if (threadIdx.x == 0 && threadIdx.y == 0) {
-            seq = halo_seq(h);
+            const unsigned seq = halo_seq(h);
             if (link_lo) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
             if (link_hi) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
         }
@@ -308,7 +306,7 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 
         const int k = kl + g.zoff;
         const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
-        if (xy_plain && kr < 0 && kl != kl_push_lo && kl != kl_push_hi) { // interior thread, interior plane
+        if (xy_plain && kr < 0) { // interior thread, interior plane: one plain store
             st4(pout, v);
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
@@ -327,10 +325,6 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 #pragma unroll
                     for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
                     st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
-                    if (zi == 0) { // boundary plane of the slab: the same row goes into the neighbour's ghost plane
-                        if (kl == kl_push_lo) st4(h.lo_plane + x0 + ys[yi] * sy, o);
-                        if (kl == kl_push_hi) st4(h.hi_plane + x0 + ys[yi] * sy, o);
-                    }
                 }
             }
         }
@@ -339,9 +333,25 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     }
     } // active
     if (link_lo || link_hi) {
+        // Push phase, kept out of the sweep loop so that the loop's register budget is the single-GPU one: each
+        // thread re-reads the rows it has just written in the slab's boundary plane (its own stores, L2 hot)
+        // and stores them into the neighbour's ghost plane over NVLink.
+        if (active) {
+            const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
+            const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;
+            const int rows[3] = {j, jr, jr2};
+#pragma unroll
+            for (int r = 0; r < 3; r++) {
+                if (rows[r] < 0) continue;
+                const long long off = x0 + rows[r] * g.sy;
+                if (link_lo) *reinterpret_cast<float4 *>(h.lo_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_begin * g.sz);
+                if (link_hi) *reinterpret_cast<float4 *>(h.hi_plane + off) = *reinterpret_cast<const float4 *>(out + off + (kl_end - 1) * g.sz);
+            }
+        }
         __syncthreads(); // every thread of the CTA has issued its peer stores
         if (threadIdx.x == 0 && threadIdx.y == 0) {
             __threadfence_system();
+            const unsigned seq = halo_seq(h); // re-read instead of carrying a register through the sweep loop
             const unsigned ctas = gridDim.x * gridDim.y;
             if (link_lo && atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ctas - 1) {
                 h.my_flags[FS_HF_CNT_LO] = 0;
