@@ -188,6 +188,49 @@ __global__ void halo_wait_kernel(const FsHaloArgs h) {
 
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
 
+// CTA-level halo steps of relax_vec4, deliberately NOT inlined: the sweep loop's register allocation must
+// not change when the exchange is compiled in (measured: inlined, the 64-register Jacobi variant lost 20%).
+__device__ __noinline__ void halo_cta_wait(const FsHaloArgs h, bool link_lo, bool link_hi) {
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        const unsigned seq = halo_seq(h);
+        if (link_lo) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
+        if (link_hi) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
+    }
+    __syncthreads();
+}
+// Push phase: each thread re-reads the rows it has just written in the slab's boundary plane (its own stores,
+// L2 hot) and stores them into the neighbour's ghost plane over NVLink; the last CTA publishes the flag.
+__device__ __noinline__ void halo_cta_push_signal(const FsHaloArgs h, const FsGrid g, const float *out, bool active, int x0,
+                                                  int j, int kl_first, int kl_last, bool link_lo, bool link_hi) {
+    if (active) {
+        const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
+        const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;
+        const int rows[3] = {j, jr, jr2};
+        for (int r = 0; r < 3; r++) {
+            if (rows[r] < 0) continue;
+            const long long off = x0 + rows[r] * g.sy;
+            if (link_lo) *reinterpret_cast<float4 *>(h.lo_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_first * g.sz);
+            if (link_hi) *reinterpret_cast<float4 *>(h.hi_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_last * g.sz);
+        }
+    }
+    __syncthreads(); // every thread of the CTA has issued its peer stores
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        __threadfence_system();
+        const unsigned seq = halo_seq(h);
+        const unsigned ctas = gridDim.x * gridDim.y;
+        if (link_lo && atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ctas - 1) {
+            h.my_flags[FS_HF_CNT_LO] = 0;
+            __threadfence_system();
+            st_release_sys(h.lo_flags + FS_HF_FROM_HI, seq);
+        }
+        if (link_hi && atomicAdd(h.my_flags + FS_HF_CNT_HI, 1u) == ctas - 1) {
+            h.my_flags[FS_HF_CNT_HI] = 0;
+            __threadfence_system();
+            st_release_sys(h.hi_flags + FS_HF_FROM_LO, seq);
+        }
+    }
+}
+
 // Gather source for the semi-Lagrangian back-trace: a field as seen from one slab -- its own planes
 // (ghosts included) plus the two neighbour slabs' copies through peer memory (NVLink loads).  A back-trace
 // that leaves even the neighbour slabs sets FS_HF_ERROR (reported by fs_sync / fs_get_field).
@@ -216,8 +259,8 @@ __device__ __forceinline__ float fs_slab_fetch(const FsSlabView &v, const FsGrid
 // Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
 // kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
-template <int MODE, bool HZ>
-__global__ void __launch_bounds__(256, 4)
+template <int MODE, bool HZ, bool HALO, bool PF>
+__global__ void __launch_bounds__(256, PF ? 3 : 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
            const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const FsHaloArgs h) {
@@ -228,22 +271,15 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     // the slab's boundary planes are mapped to blockIdx.z = 0 and 1: their halo stores and flags go out at
     // the START of the sweep and the neighbours' next sweep finds them long before it needs them.
     const int nzc = gridDim.z;
-    const int zc = blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1);
+    const int zc = !HALO ? (int)blockIdx.z : (blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1));
     const int k_lo = kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
 
     // fused halo exchange: CTAs of the first / last z chunk talk to the lower / upper neighbour slab
-    const bool link_lo = h.enabled && h.lo_flags && zc == 0;
-    const bool link_hi = h.enabled && h.hi_flags && zc == nzc - 1;
-    if (link_lo || link_hi) {
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const unsigned seq = halo_seq(h);
-            if (link_lo) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
-            if (link_hi) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
-        }
-        __syncthreads();
-    }
+    const bool link_lo = HALO && h.lo_flags && zc == 0;
+    const bool link_hi = HALO && h.hi_flags && zc == nzc - 1;
+    if (HALO && (link_lo || link_hi)) halo_cta_wait(h, link_lo, link_hi);
     if (active) {
     const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
@@ -262,24 +298,41 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     float *pout = out + idx0;
     const long long sy = g.sy, sz = g.sz;
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
+    // PF (software prefetch): the DRAM streams of plane kl+1 (centre of plane kl+2, rhs and flags of kl+1) are
+    // issued while plane kl is computed, so a thread always has two planes in flight; costs ~9 registers
+    // (3 resident CTAs per SM instead of 4).
+    float4 ahead = prev, r_cur = prev, r_nxt = prev;
+    uint32_t fl_cur = 0u, fl_nxt = 0u;
     if (!in_zero) {
         cur = ld4(pin);
         if (HZ) prev = ld4(pin - sz);
+        if (PF && HZ) next = ld4(pin + sz);
+    }
+    if (PF) {
+        if (MODE == FS_MODE_JACOBI) r_cur = ld4_stream(prh);
+        if (flags) fl_cur = ld_flags4(pfl);
     }
 
     for (int kl = k_lo; kl < k_hi; kl++, pin += sz, prh += sz, pfl += sz, pout += sz) {
         float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
         float left = 0.f, right = 0.f;
+        if (PF) {
+            if (kl + 1 < k_hi) { // streams of the next iteration
+                if (!in_zero && HZ) ahead = ld4(pin + 2 * sz);
+                if (MODE == FS_MODE_JACOBI) r_nxt = ld4_stream(prh + sz);
+                if (flags) fl_nxt = ld_flags4(pfl + sz);
+            }
+        }
         if (!in_zero) {
-            if (HZ) next = ld4(pin + sz);
+            if (!PF && HZ) next = ld4(pin + sz);
             up = ld4(pin + sy);
             dn = ld4(pin - sy);
             if (!first_x) left = __ldg(pin - 1);
             if (!last_x) right = __ldg(pin + 4);
         }
         float4 r4 = cur;
-        if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(prh);
-        const uint32_t fl = flags ? ld_flags4(pfl) : 0u;
+        if (MODE == FS_MODE_JACOBI) r4 = PF ? r_cur : ld4_stream(prh);
+        const uint32_t fl = PF ? fl_cur : (flags ? ld_flags4(pfl) : 0u);
 
         const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
         const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
@@ -330,41 +383,10 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         }
         prev = cur;
         cur = next;
+        if (PF) { next = ahead; r_cur = r_nxt; fl_cur = fl_nxt; }
     }
     } // active
-    if (link_lo || link_hi) {
-        // Push phase, kept out of the sweep loop so that the loop's register budget is the single-GPU one: each
-        // thread re-reads the rows it has just written in the slab's boundary plane (its own stores, L2 hot)
-        // and stores them into the neighbour's ghost plane over NVLink.
-        if (active) {
-            const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
-            const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;
-            const int rows[3] = {j, jr, jr2};
-#pragma unroll
-            for (int r = 0; r < 3; r++) {
-                if (rows[r] < 0) continue;
-                const long long off = x0 + rows[r] * g.sy;
-                if (link_lo) *reinterpret_cast<float4 *>(h.lo_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_begin * g.sz);
-                if (link_hi) *reinterpret_cast<float4 *>(h.hi_plane + off) = *reinterpret_cast<const float4 *>(out + off + (kl_end - 1) * g.sz);
-            }
-        }
-        __syncthreads(); // every thread of the CTA has issued its peer stores
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            __threadfence_system();
-            const unsigned seq = halo_seq(h); // re-read instead of carrying a register through the sweep loop
-            const unsigned ctas = gridDim.x * gridDim.y;
-            if (link_lo && atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ctas - 1) {
-                h.my_flags[FS_HF_CNT_LO] = 0;
-                __threadfence_system();
-                st_release_sys(h.lo_flags + FS_HF_FROM_HI, seq);
-            }
-            if (link_hi && atomicAdd(h.my_flags + FS_HF_CNT_HI, 1u) == ctas - 1) {
-                h.my_flags[FS_HF_CNT_HI] = 0;
-                __threadfence_system();
-                st_release_sys(h.hi_flags + FS_HF_FROM_LO, seq);
-            }
-        }
-    }
+    if (HALO && (link_lo || link_hi)) halo_cta_push_signal(h, g, out, active, x0, j, kl_begin, kl_end - 1, link_lo, link_hi);
 }
 
 // ---- metrics (LogCurrentMetrics, FluidSim.cs:582-594): sum of density, max |V| -------------------------
