@@ -1,0 +1,102 @@
+// NativeFluidSolver.cs -- P/Invoke binding of include/fluidsolver.h (libfluidsolver.so / fluidsolver.dll).
+//
+// Lives where the reference keeps its only other native plugin (Assets/Plugin/sqlite3.dll, consumed by
+// Mono.Data.Sqlite): the native library goes to Assets/Plugin/x86_64/libfluidsolver.so, cdecl, one entry
+// point per line of the header.  NOT compiled in the build container (no C# toolchain there); the same
+// entry points are exercised by the Python ctypes binding (3dfluidsimulation_b200/native.py) in the tests.
+//
+// Marshalling notes
+//   * float[] / byte[] are blittable: the marshaller pins them for the duration of the call, which is all the
+//     plugin requires (host pointers are only touched during the call).
+//   * bool[] is NOT blittable (4-byte BOOL by default): the obstacle mask crosses the boundary as byte[].
+//   * the solver handle is an opaque IntPtr wrapped in a SafeHandle so that a domain reload frees the GPU memory.
+using System;
+using System.Runtime.InteropServices;
+
+namespace FluidSolverNative
+{
+    public enum FsStatus { Ok = 0, BadArgument = -1, Cuda = -2, OutOfMemory = -3, Unsupported = -4, Comm = -5 }
+
+    public enum FsField
+    {
+        Density = 0, VelocityX = 1, VelocityY = 2, VelocityZ = 3,
+        VelocityX0 = 4, VelocityY0 = 5, VelocityZ0 = 6, Pressure = 7, Divergence = 8
+    }
+
+    public enum FsSolverKind { Jacobi = 0, RedBlack = 1 }
+
+    [StructLayout(LayoutKind.Sequential)]
+    public struct FsParams
+    {
+        public int abiVersion;      // FS_ABI_VERSION = 1
+        public int nx, ny, nz;      // nz == 1: the reference's 2D solver
+        public int itersDiffuse;    // 20 in the reference
+        public int itersPressure;   // 20 in the reference
+        public int solverKind;      // FsSolverKind
+        public int enableObstacle;
+        public float cellSize;      // physicalSize / currentSize
+        public float rawViscosity;  // the drag uses the unscaled viscosity
+        public int deviceId;
+        public int slabRank, slabCount;
+        public int useCudaGraph;
+        public int reserved0, reserved1, reserved2, reserved3;
+    }
+
+    public sealed class SolverHandle : SafeHandle
+    {
+        public SolverHandle() : base(IntPtr.Zero, true) { }
+        public override bool IsInvalid => handle == IntPtr.Zero;
+        protected override bool ReleaseHandle() { Native.fs_destroy(handle); return true; }
+    }
+
+    public static class Native
+    {
+        private const string Lib = "fluidsolver";
+        private const CallingConvention CC = CallingConvention.Cdecl;
+        public const int AbiVersion = 1;
+
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_abi_version();
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_create(ref FsParams p, out SolverHandle solver);
+        [DllImport(Lib, CallingConvention = CC)] public static extern void fs_destroy(IntPtr solver);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_reset(SolverHandle s);
+        [DllImport(Lib, CallingConvention = CC)] public static extern IntPtr fs_last_error(SolverHandle s);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_slab_range(SolverHandle s, out int zBegin, out int zEnd, out long ownedVoxels);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_set_obstacles(SolverHandle s, byte[] mask, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_density(SolverHandle s, float x, float y, float z, float amount);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_velocity(SolverHandle s, float x, float y, float z, float ax, float ay, float az);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_source_cells(SolverHandle s, long count, float[] x, float[] y, float[] z, float[] density, float[] ax, float[] ay, float[] az);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_sources(SolverHandle s, float[] density, float[] vx, float[] vy, float[] vz);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_step(SolverHandle s, float dt, float visc, float diff);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_sync(SolverHandle s);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_field(SolverHandle s, int field, float[] dst, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_set_field(SolverHandle s, int field, float[] src, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_metrics(SolverHandle s, out float meanDensity, out float maxSpeed, out double sumDensity);
+
+        // operator entry points (one reference job chain each); used by tests and by hosts that compose their own step
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_set_bnd(SolverHandle s, int field, int b);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_diffuse(SolverHandle s, int dst, int src, int b, float diff, float dt);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_smooth(SolverHandle s, int dst, int src, int b, float a, float c, int iters);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_lin_solve(SolverHandle s, int dst, int rhs, int b, float a, float c, int iters, int solverKind);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_project(SolverHandle s, int useV0Fields);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_advect(SolverHandle s, int dst, int src, int b, int useV0Fields, float dt);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_advect_velocity(SolverHandle s, float dt);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_op_enforce_obstacles(SolverHandle s);
+
+        // measurement + multi-GPU wiring
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_timer_start(SolverHandle s);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_timer_stop(SolverHandle s, out float elapsedMs);
+        [DllImport(Lib, CallingConvention = CC)] public static extern long fs_launch_count(SolverHandle s);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_bench_sweep(SolverHandle s, int kindAndFill, int b, int reps, out float avgMs, out double algoBytes);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_selftest_division(SolverHandle s, float divisor, ulong firstBits, ulong count, out ulong mismatches);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_halo_export(SolverHandle s, byte[] blob, long blobBytes);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_halo_connect(SolverHandle s, byte[] lowerBlob, byte[] upperBlob, int sameProcess);
+
+        /// <summary>Turns a negative status into an exception carrying fs_last_error (never thrown by the native side).</summary>
+        public static void Check(int status, SolverHandle s)
+        {
+            if (status == 0) return;
+            IntPtr msg = fs_last_error(s);
+            throw new InvalidOperationException($"fluidsolver: {(FsStatus)status}: {Marshal.PtrToStringAnsi(msg)}");
+        }
+    }
+}
