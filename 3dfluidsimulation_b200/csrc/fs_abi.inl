@@ -159,7 +159,7 @@ int fs_op_advect(fs_solver *s, int32_t dst, int32_t src, int32_t b, int32_t use_
     const float dt0 = dt * (float)(c.g.nx - 2);
     c.ex.halo_fence();
     c.ex.advect(c.g, d, d0, ux, uy, uz, c.fl(), dt0, b);
-    if (b == 3 && c.n_obst) c.ex.halo(c.g, d);
+    if (b == 3 && c.g_interior_obstacle) c.ex.halo(c.g, d);
     c.mirror(d, b);
     c.ex.halo(c.g, d);
     return c.check();
@@ -170,7 +170,7 @@ int fs_op_advect_velocity(fs_solver *s, float dt) {
     const float dt0 = dt * (float)(c.g.nx - 2);
     c.ex.halo_fence();
     c.ex.advect_velocity(c.g, c.vx, c.vy, c.vz, c.vx0, c.vy0, c.vz0, c.fl(), dt0);
-    if (c.g.hz && c.n_obst) c.ex.halo(c.g, c.vz);
+    if (c.g.hz && c.g_interior_obstacle) c.ex.halo(c.g, c.vz);
     c.mirror(c.vx, 1);
     c.mirror(c.vy, 2);
     if (c.g.hz) c.mirror(c.vz, 3);
@@ -182,7 +182,7 @@ int fs_op_advect_velocity(fs_solver *s, float dt) {
 
 int fs_op_enforce_obstacles(fs_solver *s) {
     FS_GUARD(s);
-    if (c.any_obstacle) {
+    if (c.g_any_obstacle) {
         c.ex.enforce(c.g, c.vx, c.vy, c.vz, c.flags, c.prm.cell_size, c.prm.raw_viscosity);
         c.ex.halo(c.g, c.vx);
         c.ex.halo(c.g, c.vy);

@@ -36,6 +36,9 @@ struct SolverCore {
     long long *obst_list = nullptr; // local indices of OWNED interior obstacle cells
     long long n_obst = 0;
     bool any_obstacle = false;
+    // GLOBAL obstacle presence: every slab must take the same decisions about which halo operations exist,
+    // otherwise the ranks' op sequences (and sequence numbers) diverge and the exchange deadlocks.
+    bool g_any_obstacle = false, g_interior_obstacle = false;
     std::string err;
 
     // ---- lifetime ----------------------------------------------------------------------------
@@ -88,6 +91,7 @@ struct SolverCore {
         ex.zero(flags, nloc);
         ex.free(obst_list);
         obst_list = nullptr; n_obst = 0; any_obstacle = false;
+        g_any_obstacle = g_interior_obstacle = false;
         return check();
     }
 
@@ -114,6 +118,18 @@ struct SolverCore {
                 for (int j = 1; j <= g.ny - 2; j++)
                     for (int i = 1; i <= g.nx - 2; i++)
                         if (gmask[i + j * g.sy + k * g.sz]) list.push_back(fs_idx(g, i, j, k - g.zoff));
+        g_any_obstacle = g_interior_obstacle = false;
+        {
+            const long long total = g.sz * g.nz;
+            for (long long i = 0; i < total && !g_any_obstacle; i++) g_any_obstacle = gmask[i] != 0;
+            const int gk0 = g.hz ? 1 : 0, gk1 = g.hz ? g.nz - 1 : 1;
+            for (int k = gk0; k < gk1 && g_any_obstacle && !g_interior_obstacle; k++)
+                for (int j = 1; j <= g.ny - 2 && !g_interior_obstacle; j++) {
+                    const uint8_t *row = gmask + j * g.sy + k * g.sz;
+                    for (int i = 1; i <= g.nx - 2; i++)
+                        if (row[i]) { g_interior_obstacle = true; break; }
+                }
+        }
         ex.free(obst_list);
         obst_list = nullptr;
         n_obst = (long long)list.size();
@@ -183,7 +199,7 @@ struct SolverCore {
     // sweep, [halo when the mirror reads z neighbours], mirror, halo.
     void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,
                   bool in_zero) {
-        const bool mir = b != 0 && n_obst && (b != 3 || g.hz);
+        const bool mir = b != 0 && g_interior_obstacle && (b != 3 || g.hz); // global decision, see g_interior_obstacle
         ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/!mir);
         if (mir) {
             if (b == 3) ex.halo(g, out);
@@ -243,7 +259,7 @@ struct SolverCore {
         else
             lin_solve(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true); // :1581-1582, p starts 0
         ex.gradient(g, ux, uy, uz, pressure, fl());
-        if (g.hz && n_obst) ex.halo(g, uz); // slabs: the z mirror reads the neighbours' new boundary planes
+        if (g.hz && g_interior_obstacle) ex.halo(g, uz); // slabs: the z mirror reads the neighbours' new boundary planes
         mirror(ux, 1);
         mirror(uy, 2);
         if (g.hz) mirror(uz, 3);
@@ -262,7 +278,7 @@ struct SolverCore {
         project(vx0, vy0, vz0);
         ex.halo_fence(); // slabs: the back-trace may gather from a neighbour slab, whose fields must be complete
         ex.advect_velocity(g, vx, vy, vz, vx0, vy0, vz0, fl(), dt0); // :710-711
-        if (g.hz && n_obst) ex.halo(g, vz);
+        if (g.hz && g_interior_obstacle) ex.halo(g, vz);
         mirror(vx, 1);
         mirror(vy, 2);
         if (g.hz) mirror(vz, 3);
@@ -275,7 +291,7 @@ struct SolverCore {
         ex.halo_fence();
         ex.advect(g, density, dens0, vx, vy, vz, fl(), dt0, 0);
         ex.halo(g, density);
-        if (prm.enable_obstacle && any_obstacle) { // :567-570
+        if (prm.enable_obstacle && g_any_obstacle) { // :567-570 (global decision; the kernel is a no-op where flags are 0)
             ex.enforce(g, vx, vy, vz, flags, prm.cell_size, prm.raw_viscosity);
             ex.halo(g, vx);
             ex.halo(g, vy);
