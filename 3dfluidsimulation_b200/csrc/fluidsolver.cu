@@ -25,6 +25,8 @@
 struct CudaExec {
     int dev = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_halo = nullptr;                  // side stream: the halo push runs beside the interior launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool bad = false;
     std::string msg;
@@ -77,6 +79,9 @@ struct CudaExec {
         if (device < 0 || device >= count) { msg = "device_id out of range"; bad = true; return 1; }
         FS_CUDA(cudaSetDevice(dev));
         FS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        FS_CUDA(cudaStreamCreateWithFlags(&st_halo, cudaStreamNonBlocking));
+        FS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        FS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreate(&ev0));
         FS_CUDA(cudaEventCreate(&ev1));
         FS_CUDA(cudaMalloc(&d_sum, sizeof(double)));
@@ -96,8 +101,11 @@ struct CudaExec {
         if (scratch) cudaFree(scratch);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (st_halo) cudaStreamDestroy(st_halo);
         if (st) cudaStreamDestroy(st);
-        d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = nullptr; st = nullptr;
+        d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = ev_fork = ev_join = nullptr; st = st_halo = nullptr;
     }
 
     // ---- memory -------------------------------------------------------------------------------
@@ -187,29 +195,31 @@ struct CudaExec {
             if (zchunk > 16) zchunk = 16;
             if (zchunk > cnt) zchunk = cnt;
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
-            const dim3 block(bx, by, 1), grid(gxn, gyn, nchunks);
             const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
-            FsHaloArgs h{};
-            if (halo_on && fuse_halo) { // the sweep itself waits for the neighbours, pushes its boundary planes and signals
-                const unsigned op = ++ops_since_commit;
-                h = halo_args(g, out, op);
-                pending_wait = op;
+            const dim3 block(bx, by, 1);
+#define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
+    do { const dim3 grid(gxn, gyn, NZ_); \
+         if (prefetch && HZ_) relax_vec4<MODE_, HZ_, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_); \
+         else relax_vec4<MODE_, HZ_, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_); \
+         launches++; } while (0)
+#define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
+    do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
+         else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
+            flush_halo_wait(); // slabs: the ghost planes this sweep reads must have arrived
+            if (halo_on && fuse_halo && nchunks > 2) {
+                FS_LAUNCH_RELAX_MODE(2, 0, nchunks - 1);       // the two chunks holding the slab's boundary planes
+                FS_CUDA(cudaEventRecord(ev_fork, st));         // fork: the push runs on the side stream ...
+                FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
+                halo_on_stream(g, out, st_halo);               // ... stores them into the neighbours' ghosts + signals
+                FS_CUDA(cudaEventRecord(ev_join, st_halo));
+                FS_LAUNCH_RELAX_MODE(nchunks - 2, 1, 1);       // ... while the interior chunks stream
+                FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join (also required before a graph capture ends)
             } else {
-                flush_halo_wait();
+                FS_LAUNCH_RELAX_MODE(nchunks, 0, 1);
+                if (halo_on && fuse_halo) halo(g, out);
             }
-#define FS_LAUNCH_RELAX(MODE_, HZ_, HALO_) \
-    do { if (prefetch && HZ_) relax_vec4<MODE_, HZ_, HALO_, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h); \
-         else relax_vec4<MODE_, HZ_, HALO_, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, h); } while (0)
-            const bool hl = h.enabled != 0;
-            if (mode == FS_MODE_SMOOTH) {
-                if (g.hz) { if (hl) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, true); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, false); }
-                else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, false);
-            } else {
-                if (g.hz) { if (hl) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, true); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, false); }
-                else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, false);
-            }
+#undef FS_LAUNCH_RELAX_MODE
 #undef FS_LAUNCH_RELAX
-            launches++;
             return;
         }
         if (mode == FS_MODE_SMOOTH)
@@ -391,7 +401,8 @@ struct CudaExec {
         launches++;
         pending_wait = 0;
     }
-    void halo(const FsGrid &g, float *field) {
+    void halo(const FsGrid &g, float *field) { halo_on_stream(g, field, st); }
+    void halo_on_stream(const FsGrid &g, float *field, cudaStream_t stream) {
         if (!halo_on) return;
         const unsigned op = ++ops_since_commit;
         const FsHaloArgs h = halo_args(g, field, op);
@@ -400,7 +411,7 @@ struct CudaExec {
         int blocks = (int)((plane / 4 + 255) / 256);
         if (blocks > sm_count * 2) blocks = sm_count * 2;
         if (blocks < 1 || !field) blocks = 1;
-        halo_push_kernel<<<blocks, 256, 0, st>>>(h, lo_src, hi_src, field ? plane : 0);
+        halo_push_kernel<<<blocks, 256, 0, stream>>>(h, lo_src, hi_src, field ? plane : 0);
         launches++;
         pending_wait = op;
     }

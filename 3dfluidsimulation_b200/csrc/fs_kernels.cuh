@@ -117,8 +117,11 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 //          stores into my ghosts have landed AND they no longer read the ghosts I am about to overwrite)
 //   store  my lowest owned plane -> lower neighbour's top ghost plane, my highest -> upper's plane 0
 //   signal __threadfence_system(); neighbour.flags[FROM_HI or FROM_LO] = seq
-// In relax_vec4 the three steps are done by the CTAs that own the boundary planes (first / last z chunk)
-// while every other CTA streams the interior -- the exchange overlaps the sweep tile by tile.
+// For the relaxation sweeps the order on a slab's stream is: [wait] boundary-chunk launch of relax_vec4 ->
+// halo_push_kernel (wait seq-1, store, signal seq) -> interior-chunk launch; the neighbours' next sweep finds
+// the flag set long before it needs it.  (Fusing the three steps INTO relax_vec4 was built and measured: any
+// form of it -- inlined or as noinline device functions -- cost the 64-register sweep 20-30% through register
+// pressure / lost uniform registers, see profiles/r01d_halo_variants.md, so the sweep kernel stays untouched.)
 enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_CNT_HI = 4, FS_HF_ERROR = 5, FS_HF_WORDS = 8 };
 
 struct FsHaloArgs {
@@ -188,49 +191,6 @@ __global__ void halo_wait_kernel(const FsHaloArgs h) {
 
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
 
-// CTA-level halo steps of relax_vec4, deliberately NOT inlined: the sweep loop's register allocation must
-// not change when the exchange is compiled in (measured: inlined, the 64-register Jacobi variant lost 20%).
-__device__ __noinline__ void halo_cta_wait(const FsHaloArgs h, bool link_lo, bool link_hi) {
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        const unsigned seq = halo_seq(h);
-        if (link_lo) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
-        if (link_hi) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
-    }
-    __syncthreads();
-}
-// Push phase: each thread re-reads the rows it has just written in the slab's boundary plane (its own stores,
-// L2 hot) and stores them into the neighbour's ghost plane over NVLink; the last CTA publishes the flag.
-__device__ __noinline__ void halo_cta_push_signal(const FsHaloArgs h, const FsGrid g, const float *out, bool active, int x0,
-                                                  int j, int kl_first, int kl_last, bool link_lo, bool link_hi) {
-    if (active) {
-        const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
-        const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;
-        const int rows[3] = {j, jr, jr2};
-        for (int r = 0; r < 3; r++) {
-            if (rows[r] < 0) continue;
-            const long long off = x0 + rows[r] * g.sy;
-            if (link_lo) *reinterpret_cast<float4 *>(h.lo_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_first * g.sz);
-            if (link_hi) *reinterpret_cast<float4 *>(h.hi_plane + off) = *reinterpret_cast<const float4 *>(out + off + kl_last * g.sz);
-        }
-    }
-    __syncthreads(); // every thread of the CTA has issued its peer stores
-    if (threadIdx.x == 0 && threadIdx.y == 0) {
-        __threadfence_system();
-        const unsigned seq = halo_seq(h);
-        const unsigned ctas = gridDim.x * gridDim.y;
-        if (link_lo && atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ctas - 1) {
-            h.my_flags[FS_HF_CNT_LO] = 0;
-            __threadfence_system();
-            st_release_sys(h.lo_flags + FS_HF_FROM_HI, seq);
-        }
-        if (link_hi && atomicAdd(h.my_flags + FS_HF_CNT_HI, 1u) == ctas - 1) {
-            h.my_flags[FS_HF_CNT_HI] = 0;
-            __threadfence_system();
-            st_release_sys(h.hi_flags + FS_HF_FROM_LO, seq);
-        }
-    }
-}
-
 // Gather source for the semi-Lagrangian back-trace: a field as seen from one slab -- its own planes
 // (ghosts included) plus the two neighbour slabs' copies through peer memory (NVLink loads).  A back-trace
 // that leaves even the neighbour slabs sets FS_HF_ERROR (reported by fs_sync / fs_get_field).
@@ -259,27 +219,23 @@ __device__ __forceinline__ float fs_slab_fetch(const FsSlabView &v, const FsGrid
 // Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
 // kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
-template <int MODE, bool HZ, bool HALO, bool PF>
+template <int MODE, bool HZ, bool PF>
 __global__ void __launch_bounds__(256, PF ? 3 : 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
-           const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const FsHaloArgs h) {
+           const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
+           const int zc_stride) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int x0 = gx * 4;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
-    // z chunk of this CTA.  CTAs are dispatched in blockIdx order (z slowest), so the two chunks that hold
-    // the slab's boundary planes are mapped to blockIdx.z = 0 and 1: their halo stores and flags go out at
-    // the START of the sweep and the neighbours' next sweep finds them long before it needs them.
-    const int nzc = gridDim.z;
-    const int zc = !HALO ? (int)blockIdx.z : (blockIdx.z == 0 ? 0 : (blockIdx.z == 1 ? nzc - 1 : (int)blockIdx.z - 1));
+    // z chunk of this CTA: zc_base + blockIdx.z * zc_stride.  One launch (0, 1) covers every chunk; with z-slabs the
+    // sweep is issued as two launches of this same kernel -- the two chunks that hold the slab's boundary planes
+    // first (base 0, stride nchunks-1), then the interior chunks (base 1, stride 1) -- with the P2P halo push
+    // between them, so the exchange overlaps the interior (fluidsolver.cu, CudaExec::relax).
+    const int zc = zc_base + (int)blockIdx.z * zc_stride;
     const int k_lo = kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
-
-    // fused halo exchange: CTAs of the first / last z chunk talk to the lower / upper neighbour slab
-    const bool link_lo = HALO && h.lo_flags && zc == 0;
-    const bool link_hi = HALO && h.hi_flags && zc == nzc - 1;
-    if (HALO && (link_lo || link_hi)) halo_cta_wait(h, link_lo, link_hi);
     if (active) {
     const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
@@ -386,7 +342,6 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         if (PF) { next = ahead; r_cur = r_nxt; fl_cur = fl_nxt; }
     }
     } // active
-    if (HALO && (link_lo || link_hi)) halo_cta_push_signal(h, g, out, active, x0, j, kl_begin, kl_end - 1, link_lo, link_hi);
 }
 
 // ---- metrics (LogCurrentMetrics, FluidSim.cs:582-594): sum of density, max |V| -------------------------
