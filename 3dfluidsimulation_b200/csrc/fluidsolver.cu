@@ -207,12 +207,15 @@ struct CudaExec {
          else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
             flush_halo_wait(); // slabs: the ghost planes this sweep reads must have arrived
             if (halo_on && fuse_halo && nchunks > 2) {
-                FS_LAUNCH_RELAX_MODE(2, 0, nchunks - 1);       // the two chunks holding the slab's boundary planes
-                FS_CUDA(cudaEventRecord(ev_fork, st));         // fork: the push runs on the side stream ...
+                // fork: side stream = boundary chunks, then the P2P push; main stream = interior chunks; join
+                FS_CUDA(cudaEventRecord(ev_fork, st));
                 FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
-                halo_on_stream(g, out, st_halo);               // ... stores them into the neighbours' ghosts + signals
+                { cudaStream_t main_st = st; st = st_halo;
+                  FS_LAUNCH_RELAX_MODE(2, 0, nchunks - 1);     // the two chunks holding the slab's boundary planes
+                  st = main_st; }
+                halo_on_stream(g, out, st_halo);               // stores them into the neighbours' ghosts, signals, awaits theirs
                 FS_CUDA(cudaEventRecord(ev_join, st_halo));
-                FS_LAUNCH_RELAX_MODE(nchunks - 2, 1, 1);       // ... while the interior chunks stream
+                FS_LAUNCH_RELAX_MODE(nchunks - 2, 1, 1);       // interior chunks, concurrently
                 FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join (also required before a graph capture ends)
             } else {
                 FS_LAUNCH_RELAX_MODE(nchunks, 0, 1);
@@ -413,7 +416,7 @@ struct CudaExec {
         if (blocks < 1 || !field) blocks = 1;
         halo_push_kernel<<<blocks, 256, 0, stream>>>(h, lo_src, hi_src, field ? plane : 0);
         launches++;
-        pending_wait = op;
+        (void)op; // the push kernel itself waits for the neighbours' planes of this op: nothing is left pending
     }
     void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
         if (!halo_on) return;

@@ -117,9 +117,9 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 //          stores into my ghosts have landed AND they no longer read the ghosts I am about to overwrite)
 //   store  my lowest owned plane -> lower neighbour's top ghost plane, my highest -> upper's plane 0
 //   signal __threadfence_system(); neighbour.flags[FROM_HI or FROM_LO] = seq
-// For the relaxation sweeps the order on a slab's stream is: [wait] boundary-chunk launch of relax_vec4 ->
-// halo_push_kernel (wait seq-1, store, signal seq) -> interior-chunk launch; the neighbours' next sweep finds
-// the flag set long before it needs it.  (Fusing the three steps INTO relax_vec4 was built and measured: any
+// For the relaxation sweeps a slab forks: side stream = boundary-chunk launch of relax_vec4 -> halo_push_kernel
+// (wait seq-1, store, signal seq, wait for the incoming seq); main stream = interior-chunk launch; join.  The two
+// launches run concurrently, so the exchange is hidden behind the interior chunks.  (Fusing the three steps INTO relax_vec4 was built and measured: any
 // form of it -- inlined or as noinline device functions -- cost the 64-register sweep 20-30% through register
 // pressure / lost uniform registers, see profiles/r01d_halo_variants.md, so the sweep kernel stays untouched.)
 enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_CNT_HI = 4, FS_HF_ERROR = 5, FS_HF_WORDS = 8 };
@@ -178,6 +178,10 @@ halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const flo
             __threadfence_system();
             if (h.lo_flags) st_release_sys(h.lo_flags + FS_HF_FROM_HI, s_seq);
             if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
+            // ... and do not retire before the neighbours' planes of the same op have landed here: whatever
+            // is ordered after this kernel may read the ghost planes (no separate wait launch needed)
+            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq);
+            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq);
         }
     }
 }
