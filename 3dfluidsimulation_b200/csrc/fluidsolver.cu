@@ -246,10 +246,41 @@ struct CudaExec {
     void mirror(const FsGrid &g, float *x, const uint8_t *flags, const long long *list, long long n, int b) {
         linear(n, [=] __device__(long long t) { fs_mirror_cell(g, x, flags, b, list[t]); });
     }
+    // launch geometry of the one-plane-per-thread float4 kernels
+    bool vec4_geometry(const FsGrid &g, dim3 *grid, dim3 *block, int *kl0) {
+        int cnt;
+        interior_planes(g, kl0, &cnt);
+        if (cnt <= 0 || g.nx % 4 != 0 || force_generic) return false;
+        const int groups = g.nx / 4;
+        int bx = 32;
+        while (bx / 2 >= groups && bx > 1) bx /= 2;
+        const int by = 256 / bx;
+        *block = dim3(bx, by, 1);
+        *grid = dim3((groups + bx - 1) / bx, (g.ny - 2 + by - 1) / by, cnt);
+        return true;
+    }
     void divergence(const FsGrid &g, float *div, const float *ux, const float *uy, const float *uz) {
+        dim3 grid, block;
+        int kl0;
+        if (vec4_geometry(g, &grid, &block, &kl0)) {
+            flush_halo_wait();
+            if (g.hz) divergence_vec4<true><<<grid, block, 0, st>>>(g, div, ux, uy, uz, kl0);
+            else divergence_vec4<false><<<grid, block, 0, st>>>(g, div, ux, uy, uz, kl0);
+            launches++;
+            return;
+        }
         cells(g, [=] __device__(int i, int j, int kl) { fs_divergence_cell(g, div, ux, uy, uz, i, j, kl); });
     }
     void gradient(const FsGrid &g, float *ux, float *uy, float *uz, const float *p, const uint8_t *flags) {
+        dim3 grid, block;
+        int kl0;
+        if (vec4_geometry(g, &grid, &block, &kl0)) {
+            flush_halo_wait();
+            if (g.hz) gradient_vec4<true><<<grid, block, 0, st>>>(g, ux, uy, uz, p, flags, kl0);
+            else gradient_vec4<false><<<grid, block, 0, st>>>(g, ux, uy, uz, p, flags, kl0);
+            launches++;
+            return;
+        }
         cells(g, [=] __device__(int i, int j, int kl) { fs_gradient_cell(g, ux, uy, uz, p, flags, i, j, kl); });
     }
     FsSlabView slab_view(const FsGrid &g, const float *field) const {
@@ -267,7 +298,7 @@ struct CudaExec {
                 const uint8_t *flags, float dt0, int b) {
         const FsSlabView v = slab_view(g, d0);
         cells(g, [=] __device__(int i, int j, int kl) {
-            auto samp = [&](int ii, int jj, int kk) { return fs_slab_fetch(v, g, ii, jj, kk); };
+            auto samp = [&](int kk) { return fs_slab_plane(v, g, kk); };
             fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
         });
     }
@@ -275,9 +306,9 @@ struct CudaExec {
                          const float *sz, const uint8_t *flags, float dt0) {
         const FsSlabView vx_ = slab_view(g, sx), vy_ = slab_view(g, sy), vz_ = g.hz ? slab_view(g, sz) : FsSlabView{};
         cells(g, [=] __device__(int i, int j, int kl) {
-            auto px = [&](int ii, int jj, int kk) { return fs_slab_fetch(vx_, g, ii, jj, kk); };
-            auto py = [&](int ii, int jj, int kk) { return fs_slab_fetch(vy_, g, ii, jj, kk); };
-            auto pz = [&](int ii, int jj, int kk) { return fs_slab_fetch(vz_, g, ii, jj, kk); };
+            auto px = [&](int kk) { return fs_slab_plane(vx_, g, kk); };
+            auto py = [&](int kk) { return fs_slab_plane(vy_, g, kk); };
+            auto pz = [&](int kk) { return fs_slab_plane(vz_, g, kk); };
             fs_advect_velocity_cell(g, dx, dy, dz, px, py, pz, sx, sy, sz, flags, dt0, i, j, kl);
         });
     }

@@ -198,8 +198,7 @@ FS_HD void fs_gradient_cell(const FsGrid &g, float *vx, float *vy, float *vz, co
 }
 
 // ---- advection -------------------------------------------------------------------------------------
-// AdvectJob :1138-1185: back-trace, clamp, bi/trilinear weights.  `samp(ii,jj,kk)` fetches the
-// advected field at GLOBAL integer coordinates (it resolves slab ownership).
+// AdvectJob :1138-1185: back-trace, clamp, bi/trilinear weights.
 struct FsAdvectWeights {
     int i0, j0, k0;
     float s0, s1, t0, t1, u0, u1;
@@ -234,15 +233,19 @@ FS_HD FsAdvectWeights fs_advect_weights(const FsGrid &g, float dt0, float velx, 
     return w;
 }
 
-template <class Samp>
-FS_HD float fs_advect_interp(const FsGrid &g, const FsAdvectWeights &w, Samp samp) {
-    const int i0 = w.i0, i1 = w.i0 + 1, j0 = w.j0, j1 = w.j0 + 1;
-    const float lo = w.s0 * (w.t0 * samp(i0, j0, w.k0) + w.t1 * samp(i0, j1, w.k0)) +
-                     w.s1 * (w.t0 * samp(i1, j0, w.k0) + w.t1 * samp(i1, j1, w.k0)); // :1183-1184
+// `plane(kk)` returns the base pointer of GLOBAL plane kk of the advected field (it resolves slab ownership:
+// local planes, or the neighbour slab's copy through peer memory), so that the 4 gathers of one plane
+// share one address computation.
+template <class Plane>
+FS_HD float fs_advect_interp(const FsGrid &g, const FsAdvectWeights &w, Plane plane) {
+    const long long o = w.i0 + w.j0 * g.sy;
+    const float *p0 = plane(w.k0);
+    const float lo = w.s0 * (w.t0 * p0[o] + w.t1 * p0[o + g.sy]) +
+                     w.s1 * (w.t0 * p0[o + 1] + w.t1 * p0[o + g.sy + 1]); // :1183-1184
     if (!g.hz) return lo;
-    const int k1 = w.k0 + 1;
-    const float hi = w.s0 * (w.t0 * samp(i0, j0, k1) + w.t1 * samp(i0, j1, k1)) +
-                     w.s1 * (w.t0 * samp(i1, j0, k1) + w.t1 * samp(i1, j1, k1));
+    const float *p1 = plane(w.k0 + 1);
+    const float hi = w.s0 * (w.t0 * p1[o] + w.t1 * p1[o + g.sy]) +
+                     w.s1 * (w.t0 * p1[o + 1] + w.t1 * p1[o + g.sy + 1]);
     return w.u0 * lo + w.u1 * hi;
 }
 

@@ -203,20 +203,17 @@ struct FsSlabView {
     int zoff, nzl, lo_zoff, lo_nzl, hi_zoff, hi_nzl;
     unsigned *err;
 };
-__device__ __forceinline__ float fs_slab_fetch(const FsSlabView &v, const FsGrid &g, int ii, int jj, int kk) {
+__device__ __forceinline__ const float *fs_slab_plane(const FsSlabView &v, const FsGrid &g, int kk) {
     int kl = kk - v.zoff;
-    const float *base = v.loc;
-    if (kl < 0) {
-        base = v.lo; kl = kk - v.lo_zoff;
-        if (!base || kl < 0) { if (v.err) *v.err = 1u; return 0.0f; }
-        return base[ii + jj * g.sy + kl * g.sz];
+    if (kl >= 0 && kl < v.nzl) return v.loc + kl * g.sz;
+    const float *base = kl < 0 ? v.lo : v.hi;
+    const int pl = kl < 0 ? kk - v.lo_zoff : kk - v.hi_zoff;
+    const int pn = kl < 0 ? v.lo_nzl : v.hi_nzl;
+    if (!base || pl < 0 || pl >= pn) { // the back-trace left even the neighbour slab: flag it, read something valid
+        if (v.err) *v.err = 1u;
+        return v.loc;
     }
-    if (kl >= v.nzl) {
-        base = v.hi; kl = kk - v.hi_zoff;
-        if (!base || kl >= v.hi_nzl) { if (v.err) *v.err = 1u; return 0.0f; }
-        return base[ii + jj * g.sy + kl * g.sz];
-    }
-    return __ldg(base + ii + jj * g.sy + kl * g.sz);
+    return base + pl * g.sz;
 }
 
 // ---- the hot sweep ---------------------------------------------------------------------------------
@@ -346,6 +343,121 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         if (PF) { next = ahead; r_cur = r_nxt; fl_cur = fl_nxt; }
     }
     } // active
+}
+
+// ---- float4 versions of the once-per-step stencils --------------------------------------------------------
+// Same thread mapping as relax_vec4 (a float4 of x per thread, nx % 4 == 0), one plane per thread.
+struct FsVec4Pos {
+    int x0, j, kl, jr, jr2, kr, kr2;
+    bool first_x, last_x;
+};
+__device__ __forceinline__ FsVec4Pos fs_vec4_pos(const FsGrid &g, int x0, int j, int kl) {
+    FsVec4Pos p;
+    p.x0 = x0; p.j = j; p.kl = kl;
+    p.first_x = x0 == 0; p.last_x = x0 + 4 == g.nx;
+    p.jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
+    p.jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1;
+    const int k = kl + g.zoff;
+    p.kr = g.hz ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
+    p.kr2 = (g.hz && k == 1 && k == g.nz - 2) ? kl + 1 : -1;
+    return p;
+}
+// Stores the row and every set_bnd ring row / lane that derives from it (ring scatter, b = field kind).
+__device__ __forceinline__ void fs_vec4_store_ring(float *out, const FsGrid &g, const FsVec4Pos &p, float v[4], int b) {
+    if (!p.first_x && !p.last_x && p.jr < 0 && p.kr < 0) {
+        st4(out + fs_idx(g, p.x0, p.j, p.kl), v);
+        return;
+    }
+    if (p.first_x) v[0] = v[1];
+    if (p.last_x) v[3] = v[2];
+    const int fxl[4] = {p.first_x ? 1 : 0, 0, 0, p.last_x ? 1 : 0};
+    const int zs[3] = {p.kl, p.kr, p.kr2}, ys[3] = {p.j, p.jr, p.jr2};
+#pragma unroll
+    for (int zi = 0; zi < 3; zi++) {
+        if (zi > 0 && zs[zi] < 0) continue;
+#pragma unroll
+        for (int yi = 0; yi < 3; yi++) {
+            if (yi > 0 && ys[yi] < 0) continue;
+            float o[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], yi > 0, zi > 0, b);
+            st4(out + fs_idx(g, p.x0, ys[yi], zs[zi]), o);
+        }
+    }
+}
+
+// ProjectDivergenceJob :1080-1095 + BoundaryJob(b = 0); 20 B/voxel in 3D (p = 0 is not stored).
+template <bool HZ>
+__global__ void __launch_bounds__(256)
+divergence_vec4(const FsGrid g, float *__restrict__ div, const float *__restrict__ vx, const float *__restrict__ vy,
+                const float *__restrict__ vz, const int kl0) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = kl0 + blockIdx.z;
+    if (x0 >= g.nx || j > g.ny - 2) return;
+    const FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl);
+    const long long idx = fs_idx(g, x0, j, kl);
+    const float4 c = ld4(vx + idx), yt = ld4(vy + idx + g.sy), yb = ld4(vy + idx - g.sy);
+    const float left = pos.first_x ? 0.f : __ldg(vx + idx - 1), right = pos.last_x ? 0.f : __ldg(vx + idx + 4);
+    float4 zu = make_float4(0.f, 0.f, 0.f, 0.f), zd = zu;
+    if (HZ) { zu = ld4(vz + idx + g.sz); zd = ld4(vz + idx - g.sz); }
+    const float xs[6] = {left, c.x, c.y, c.z, c.w, right};
+    const float ytv[4] = {yt.x, yt.y, yt.z, yt.w}, ybv[4] = {yb.x, yb.y, yb.z, yb.w};
+    const float zuv[4] = {zu.x, zu.y, zu.z, zu.w}, zdv[4] = {zd.x, zd.y, zd.z, zd.w};
+    const FsDivisor dn = fs_make_divisor((float)g.nx);
+    float v[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        float s = ((xs[l + 2] - xs[l]) + ytv[l]) - ybv[l];
+        if (HZ) s = (s + zuv[l]) - zdv[l];
+        v[l] = fs_div(-0.5f * s, dn);
+    }
+    fs_vec4_store_ring(div, g, pos, v, 0);
+}
+
+// ProjectVelocityAdjustJob :1107-1122 + BoundaryJob(b = 1/2/3) faces, in place; 29 B/voxel in 3D.
+template <bool HZ>
+__global__ void __launch_bounds__(256)
+gradient_vec4(const FsGrid g, float *vx, float *vy, float *vz, const float *__restrict__ p,
+              const uint8_t *__restrict__ flags, const int kl0) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = kl0 + blockIdx.z;
+    if (x0 >= g.nx || j > g.ny - 2) return;
+    const FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl);
+    const long long idx = fs_idx(g, x0, j, kl);
+    const float nf = (float)g.nx;
+    const float4 pc = ld4(p + idx), pt = ld4(p + idx + g.sy), pb = ld4(p + idx - g.sy);
+    const float pl = pos.first_x ? 0.f : __ldg(p + idx - 1), pr = pos.last_x ? 0.f : __ldg(p + idx + 4);
+    const uint32_t fl = flags ? ld_flags4(flags + idx) : 0u;
+    const float ps[6] = {pl, pc.x, pc.y, pc.z, pc.w, pr};
+    const float ptv[4] = {pt.x, pt.y, pt.z, pt.w}, pbv[4] = {pb.x, pb.y, pb.z, pb.w};
+    {
+        const float4 u = ld4_plain(vx + idx);
+        float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            if (!((fl >> (8 * l)) & 1u)) v[l] = v[l] - 0.5f * (ps[l + 2] - ps[l]) * nf;
+        fs_vec4_store_ring(vx, g, pos, v, 1);
+    }
+    {
+        const float4 u = ld4_plain(vy + idx);
+        float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            if (!((fl >> (8 * l)) & 1u)) v[l] = v[l] - 0.5f * (ptv[l] - pbv[l]) * nf;
+        fs_vec4_store_ring(vy, g, pos, v, 2);
+    }
+    if (HZ) {
+        const float4 pu = ld4(p + idx + g.sz), pd = ld4(p + idx - g.sz);
+        const float puv[4] = {pu.x, pu.y, pu.z, pu.w}, pdv[4] = {pd.x, pd.y, pd.z, pd.w};
+        const float4 u = ld4_plain(vz + idx);
+        float v[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            if (!((fl >> (8 * l)) & 1u)) v[l] = v[l] - 0.5f * (puv[l] - pdv[l]) * nf;
+        fs_vec4_store_ring(vz, g, pos, v, 3);
+    }
 }
 
 // ---- metrics (LogCurrentMetrics, FluidSim.cs:582-594): sum of density, max |V| -------------------------

@@ -81,16 +81,16 @@ struct HostExec {
     void advect(const FsGrid &g, float *d, const float *d0, const float *ux, const float *uy, const float *uz,
                 const uint8_t *flags, float dt0, int b) {
         cells(g, [&](int i, int j, int kl) {
-            auto samp = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, d0, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
+            auto samp = [&](int kk) { int l; const float *b = resolve(g, d0, kk, &l); return b + l * g.sz; };
             fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
         });
     }
     void advect_velocity(const FsGrid &g, float *dx, float *dy, float *dz, const float *sx, const float *sy,
                          const float *sz, const uint8_t *flags, float dt0) {
         cells(g, [&](int i, int j, int kl) {
-            auto px = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sx, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
-            auto py = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sy, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
-            auto pz = [&](int ii, int jj, int kk) { int l; const float *b = resolve(g, sz, kk, &l); return b[fs_idx(g, ii, jj, l)]; };
+            auto px = [&](int kk) { int l; const float *b = resolve(g, sx, kk, &l); return b + l * g.sz; };
+            auto py = [&](int kk) { int l; const float *b = resolve(g, sy, kk, &l); return b + l * g.sz; };
+            auto pz = [&](int kk) { int l; const float *b = resolve(g, sz, kk, &l); return b + l * g.sz; };
             fs_advect_velocity_cell(g, dx, dy, dz, px, py, pz, sx, sy, sz, flags, dt0, i, j, kl);
         });
     }
