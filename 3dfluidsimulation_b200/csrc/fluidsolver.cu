@@ -32,6 +32,8 @@ struct CudaExec {
     std::string msg;
     int64_t launches = 0;
     bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
+    int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
+                                // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
     bool prefetch = false;      // FS_RELAX_PREFETCH=1: software-prefetch sweep variant (measured slower: 336 vs 292 us, fewer resident CTAs)
     bool use_graph = false;
     int sm_count = 148;
@@ -89,6 +91,8 @@ struct CudaExec {
         FS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         const char *fg = getenv("FS_FORCE_GENERIC");
         force_generic = fg && fg[0] == '1';
+        const char *la = getenv("FS_L2_AHEAD");
+        if (la) l2_ahead = atoi(la);
         const char *pf = getenv("FS_RELAX_PREFETCH");
         if (pf) prefetch = pf[0] != '0';
         return bad ? 1 : 0;
@@ -199,8 +203,8 @@ struct CudaExec {
             const dim3 block(bx, by, 1);
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, NZ_); \
-         if (prefetch && HZ_) relax_vec4<MODE_, HZ_, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_); \
-         else relax_vec4<MODE_, HZ_, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_); \
+         if (prefetch && HZ_) relax_vec4<MODE_, HZ_, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
+         else relax_vec4<MODE_, HZ_, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
          launches++; } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \

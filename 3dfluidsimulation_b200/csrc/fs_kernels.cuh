@@ -39,6 +39,7 @@ __device__ __forceinline__ float4 ld4_stream(const float *p) { // read once: do 
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ float4 ld4_plain(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 __device__ __forceinline__ uint32_t ld_flags4(const uint8_t *p) {
     uint32_t r;
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(256, PF ? 3 : 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
            const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
-           const int zc_stride) {
+           const int zc_stride, const int l2_ahead) {
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int x0 = gx * 4;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -286,6 +287,10 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
             dn = ld4(pin - sy);
             if (!first_x) left = __ldg(pin - 1);
             if (!last_x) right = __ldg(pin + 4);
+        }
+        if (l2_ahead > 0 && kl + l2_ahead <= k_hi) { // start the DRAM->L2 transfer of a later plane (no registers held)
+            if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
+            if (MODE == FS_MODE_JACOBI) prefetch_l2(prh + (long long)l2_ahead * sz);
         }
         float4 r4 = cur;
         if (MODE == FS_MODE_JACOBI) r4 = PF ? r_cur : ld4_stream(prh);
