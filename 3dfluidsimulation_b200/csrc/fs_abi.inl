@@ -211,7 +211,8 @@ int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps,
     if (fill == 1) { c.ex.fill_random(c.vx0, c.nloc, 1u); c.ex.fill_random(c.vy0, c.nloc, 2u); }
     if (fill == 2) { c.ex.zero(c.vx0, sizeof(float) * c.nloc); c.ex.zero(c.vy0, sizeof(float) * c.nloc); }
     const long long interior = (long long)(c.g.nx) * c.g.ny * (c.ze - c.zb);
-    const double per_voxel = kind == 0 ? 9.0 : 13.0;
+    // smoother 4 R + 4 W, Jacobi 8 R + 4 W, + 1 flag byte when the grid has obstacles
+    const double per_voxel = (kind == 0 ? 8.0 : 12.0) + (c.fl() ? 1.0 : 0.0);
     float a, cc;
     SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
     auto once = [&]() {

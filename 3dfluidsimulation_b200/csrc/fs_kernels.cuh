@@ -288,9 +288,11 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
             if (!first_x) left = __ldg(pin - 1);
             if (!last_x) right = __ldg(pin + 4);
         }
-        if (l2_ahead > 0 && kl + l2_ahead <= k_hi) { // start the DRAM->L2 transfer of a later plane (no registers held)
+        if (l2_ahead > 0 && kl + l2_ahead < k_hi) { // planes of iteration kl + l2_ahead (all inside this chunk's range)
+            // start the DRAM->L2 transfers of a later iteration now; unlike a register prefetch this holds no registers
             if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
             if (MODE == FS_MODE_JACOBI) prefetch_l2(prh + (long long)l2_ahead * sz);
+            if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
         }
         float4 r4 = cur;
         if (MODE == FS_MODE_JACOBI) r4 = PF ? r_cur : ld4_stream(prh);
