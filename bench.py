@@ -11,9 +11,10 @@ the N GPUs (strong scaling: the grid is fixed).  The state (6 GB) is far larger 
 explicit L2 flush is needed between timed steps.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel = the 3D Jacobi sweep (relax_vec4): algorithmic 13 B/voxel * voxels per
-                launch / average launch duration (CUDA events on the solver's stream, measured live
-                in this process right after the timed steps), against MEASURED_PEAKS.json hbm_gbs.
+  roofline      dominant kernel = the 3D Jacobi sweep (relax_vec4): algorithmic 13 B/voxel (12 without
+                obstacles: no flag stream) * voxels per launch / average launch duration (CUDA events on the
+                solver's stream, 20 back-to-back launches on the live fields in this process right after the
+                timed steps), against MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes (profiles/).
   cpu_baseline  the CPU oracle (C restatement of FluidSim.cs, OpenMP) on a bounded sample (rank 0, N=1)
   e2e           same metric through the C ABI with HOST buffers: per step the source cells go host->
                 device and density + pressure (what UpdateVisualization reads, FluidSim.cs:761-768)
@@ -324,7 +325,7 @@ def main():
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = 128 if n >= 128 else n
-        csteps = 2
+        csteps = 8
         val, cms = cpu_oracle_rate(sample, kd, kp, csteps, 1)
         line["cpu_baseline"] = {"value": val, "unit": "Gvoxel-updates/s", "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{sample}^3 sub-grid, same K_d/K_p, {csteps} steps after 1 warm-up ({cms:.0f} ms/step)"}
