@@ -34,7 +34,6 @@ struct CudaExec {
     bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
-    bool prefetch = false;      // FS_RELAX_PREFETCH=1: software-prefetch sweep variant (measured slower: 336 vs 292 us, fewer resident CTAs)
     bool use_graph = false;
     int sm_count = 148;
 
@@ -93,8 +92,6 @@ struct CudaExec {
         force_generic = fg && fg[0] == '1';
         const char *la = getenv("FS_L2_AHEAD");
         if (la) l2_ahead = atoi(la);
-        const char *pf = getenv("FS_RELAX_PREFETCH");
-        if (pf) prefetch = pf[0] != '0';
         return bad ? 1 : 0;
     }
     void close() {
@@ -203,8 +200,7 @@ struct CudaExec {
             const dim3 block(bx, by, 1);
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, NZ_); \
-         if (prefetch && HZ_) relax_vec4<MODE_, HZ_, true><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
-         else relax_vec4<MODE_, HZ_, false><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
+         relax_vec4<MODE_, HZ_><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
          launches++; } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
@@ -408,7 +404,6 @@ struct CudaExec {
     unsigned *my_flags = nullptr;       // FS_HF_WORDS words, device
     std::vector<float *> bufs;          // this slab's field allocations, same order on every rank
     unsigned ops_since_commit = 0;      // halo ops enqueued since the last halo_commit
-    unsigned pending_wait = 0;          // op offset whose completion by the neighbours nobody has waited for yet
 
     int buf_index(const float *p) const {
         for (size_t i = 0; i < bufs.size(); i++)
@@ -432,13 +427,9 @@ struct CudaExec {
         }
         return h;
     }
-    // Consumers without a fused wait (every kernel except relax_vec4) must see the neighbours' last op.
-    void flush_halo_wait() {
-        if (!halo_on || !pending_wait) return;
-        halo_wait_kernel<<<1, 1, 0, st>>>(halo_args(FsGrid{}, nullptr, pending_wait));
-        launches++;
-        pending_wait = 0;
-    }
+    // Every halo_push_kernel retires only after the neighbours' planes of the same op have landed, so kernels
+    // ordered after it can read the ghost planes without any further wait.
+    void flush_halo_wait() {}
     void halo(const FsGrid &g, float *field) { halo_on_stream(g, field, st); }
     void halo_on_stream(const FsGrid &g, float *field, cudaStream_t stream) {
         if (!halo_on) return;

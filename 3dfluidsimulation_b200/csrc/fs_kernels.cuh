@@ -187,13 +187,6 @@ halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const flo
     }
 }
 
-// Consumer side for kernels without a fused wait: returns when both neighbours have completed op seq.
-__global__ void halo_wait_kernel(const FsHaloArgs h) {
-    const unsigned seq = halo_seq(h);
-    if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq);
-    if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq);
-}
-
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
 
 // Gather source for the semi-Lagrangian back-trace: a field as seen from one slab -- its own planes
@@ -219,10 +212,12 @@ __device__ __forceinline__ const float *fs_slab_plane(const FsSlabView &v, const
 
 // ---- the hot sweep ---------------------------------------------------------------------------------
 // Requirements: nx % 4 == 0 (so every row start is 16-byte aligned in a cudaMalloc'd array).
+// Latency hiding: prefetch.global.L2 of the planes l2_ahead iterations ahead (holds no registers; 297 -> 246 us at
+// 512^3).  A register prefetch of the next plane was measured and rejected (78 registers -> 3 CTAs/SM, 336 us).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
 // kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
-template <int MODE, bool HZ, bool PF>
-__global__ void __launch_bounds__(256, PF ? 3 : 4)
+template <int MODE, bool HZ>
+__global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
            float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
            const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
@@ -256,33 +251,16 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     float *pout = out + idx0;
     const long long sy = g.sy, sz = g.sz;
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
-    // PF (software prefetch): the DRAM streams of plane kl+1 (centre of plane kl+2, rhs and flags of kl+1) are
-    // issued while plane kl is computed, so a thread always has two planes in flight; costs ~9 registers
-    // (3 resident CTAs per SM instead of 4).
-    float4 ahead = prev, r_cur = prev, r_nxt = prev;
-    uint32_t fl_cur = 0u, fl_nxt = 0u;
     if (!in_zero) {
         cur = ld4(pin);
         if (HZ) prev = ld4(pin - sz);
-        if (PF && HZ) next = ld4(pin + sz);
-    }
-    if (PF) {
-        if (MODE == FS_MODE_JACOBI) r_cur = ld4_stream(prh);
-        if (flags) fl_cur = ld_flags4(pfl);
     }
 
     for (int kl = k_lo; kl < k_hi; kl++, pin += sz, prh += sz, pfl += sz, pout += sz) {
         float4 up = make_float4(0.f, 0.f, 0.f, 0.f), dn = up;
         float left = 0.f, right = 0.f;
-        if (PF) {
-            if (kl + 1 < k_hi) { // streams of the next iteration
-                if (!in_zero && HZ) ahead = ld4(pin + 2 * sz);
-                if (MODE == FS_MODE_JACOBI) r_nxt = ld4_stream(prh + sz);
-                if (flags) fl_nxt = ld_flags4(pfl + sz);
-            }
-        }
         if (!in_zero) {
-            if (!PF && HZ) next = ld4(pin + sz);
+            if (HZ) next = ld4(pin + sz);
             up = ld4(pin + sy);
             dn = ld4(pin - sy);
             if (!first_x) left = __ldg(pin - 1);
@@ -295,8 +273,8 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
             if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
         }
         float4 r4 = cur;
-        if (MODE == FS_MODE_JACOBI) r4 = PF ? r_cur : ld4_stream(prh);
-        const uint32_t fl = PF ? fl_cur : (flags ? ld_flags4(pfl) : 0u);
+        if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(prh);
+        const uint32_t fl = flags ? ld_flags4(pfl) : 0u;
 
         const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
         const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
@@ -347,7 +325,6 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
         }
         prev = cur;
         cur = next;
-        if (PF) { next = ahead; r_cur = r_nxt; fl_cur = fl_nxt; }
     }
     } // active
 }

@@ -145,6 +145,7 @@ def cpu_oracle_rate(n, kd, kp, steps, warmup=1):
     """Times the CPU oracle (OpenMP over all host cores) on an n^3 sample of the workload."""
     import oracle
 
+    oracle.set_threads(os.cpu_count())  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     o = oracle.OracleSolver(n, n, n, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=True, cell_size=1.0 / n)
     o.obstacles[...] = sphere_mask(n, n)
     x, y, z, fall = plume(n, n)

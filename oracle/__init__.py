@@ -55,6 +55,15 @@ def lib() -> C.CDLL:
     return _lib
 
 
+def set_threads(n: int | None = None) -> int:
+    """OpenMP thread count for the oracle's sweeps (torchrun exports OMP_NUM_THREADS=1, which would make the CPU
+    baseline single threaded).  Default: every host core."""
+    n = int(n or os.cpu_count() or 1)
+    lib()
+    C.CDLL("libgomp.so.1").omp_set_num_threads(n)
+    return n
+
+
 def _f(a):
     if a is None:
         return None

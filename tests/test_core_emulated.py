@@ -46,6 +46,12 @@ def test_steps(emul_lib, oracle, dims, steps, kd, kp, obstacles):
     P.case_steps(emul_lib, oracle, *dims, steps, kd=kd, kp=kp, obstacles=obstacles)
 
 
+@pytest.mark.parametrize("kd,kp", [(3, 5), (1, 1), (0, 0)])
+def test_odd_iteration_counts_rotate_buffer_roles(emul_lib, oracle, kd, kp):
+    P.case_steps(emul_lib, oracle, 12, 10, 9, 4, kd=kd, kp=kp, obstacles=False)
+    P.case_steps(emul_lib, oracle, 12, 10, 1, 4, kd=kd, kp=kp, obstacles=True)
+
+
 @pytest.mark.parametrize("name", ["kernels2d_n24.npz", "kernels2d_n30.npz"])
 def test_golden_kernels(emul_lib, name):
     P.case_golden_2d(emul_lib, name)

@@ -66,6 +66,14 @@ def test_golden_trajectory(lib, name, graph):
     P.case_golden_trajectory(lib, name, use_graph=graph)
 
 
+@pytest.mark.parametrize("kd,kp", [(3, 5), (1, 1), (2, 3)])
+def test_graph_replay_with_rotating_buffer_roles(lib, oracle, kd, kp):
+    """Odd iteration counts leave the ping-pong buffers swapped after a step, so consecutive steps need different
+    captured graphs (keyed by the role configuration); 6 steps must still follow the oracle."""
+    P.case_steps(lib, oracle, 16, 12, 10, 6, kd=kd, kp=kp, obstacles=False, use_graph=True)
+    P.case_steps(lib, oracle, 16, 12, 1, 6, kd=kd, kp=kp, obstacles=True, use_graph=True)
+
+
 @pytest.mark.parametrize("obstacles", [True, False])
 def test_config1_32cube_trajectory(lib, oracle, obstacles):
     """BASELINE config 1: 32^3 smoke plume, K_d = K_p = 20, dt = 0.1 (10 steps here, CFL <~ 3)."""
