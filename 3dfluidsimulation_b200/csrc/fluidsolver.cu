@@ -231,10 +231,22 @@ struct CudaExec {
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         if (fuse_halo) halo(g, out); // per-cell fallback has no fused exchange
     }
-    void rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour) {
+    // returns true when the launch also performed set_bnd (colour 1 of the float4 kernel)
+    bool rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour, int b) {
+        dim3 grid, block;
+        int kl0;
+        const bool c_ok = c != 0.0f && c == c && c - c == 0.0f;
+        if (c_ok && vec4_geometry(g, &grid, &block, &kl0)) {
+            const int ring = colour == 1 ? 1 : 0;
+            if (g.hz) rb_vec4<true><<<grid, block, 0, st>>>(g, x, rhs, flags, a, c, colour, b, ring, kl0);
+            else rb_vec4<false><<<grid, block, 0, st>>>(g, x, rhs, flags, a, c, colour, b, ring, kl0);
+            launches++;
+            return ring != 0;
+        }
         cells(g, [=] __device__(int i, int j, int kl) {
             if (((i + j + kl + g.zoff) & 1) == colour) fs_rb_cell(g, x, rhs, flags, a, c, i, j, kl);
         });
+        return false;
     }
     void bnd(const FsGrid &g, float *x, int b) {
         cells(g, [=] __device__(int i, int j, int kl) {

@@ -216,7 +216,7 @@ int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps,
     float a, cc;
     SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
     auto once = [&]() {
-        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1); }
+        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0, b); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1, b); }
         else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false, true);
     };
     for (int w = 0; w < 2; w++) once(); // warm-up

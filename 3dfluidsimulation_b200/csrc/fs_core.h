@@ -235,11 +235,12 @@ struct SolverCore {
     void lin_solve_rb(int b, float *x, const float *rhs, float a, float c, int iters, bool zero_guess) {
         if (zero_guess) ex.zero(x, sizeof(float) * nloc);
         for (int it = 0; it < iters; it++) {
+            bool ringed = false;
             for (int colour = 0; colour < 2; colour++) {
-                ex.rb_half(g, x, rhs, fl(), a, c, colour);
+                ringed = ex.rb_half(g, x, rhs, fl(), a, c, colour, b);
                 ex.halo(g, x);
             }
-            ex.bnd(g, x, b);
+            if (!ringed) ex.bnd(g, x, b); // the float4 kernel writes the set_bnd ring in its colour-1 launch
             mirror(x, b);
             if (b != 0) ex.halo(g, x);
         }

@@ -444,6 +444,49 @@ gradient_vec4(const FsGrid g, float *vx, float *vy, float *vz, const float *__re
     }
 }
 
+// Red-black Gauss-Seidel half sweep (BASELINE config 5; oracle fo_lin_solve_rb), float4 per thread, in place.
+// A cell of colour (i+j+k)&1 reads only cells of the other colour, which no thread writes in this launch, so
+// the update order is free.  The colour-1 launch also performs set_bnd (ring scatter from the now final row),
+// so a full sweep is two launches and 26 B/voxel (a fused single-pass form is the next step).
+template <bool HZ>
+__global__ void __launch_bounds__(256)
+rb_vec4(const FsGrid g, float *x, const float *__restrict__ rhs, const uint8_t *__restrict__ flags, const float a,
+        const float c, const int colour, const int b, const int write_ring, const int kl0) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = kl0 + blockIdx.z;
+    if (x0 >= g.nx || j > g.ny - 2) return;
+    FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl);
+    const long long idx = fs_idx(g, x0, j, kl);
+    const float4 cur = ld4_plain(x + idx), up = ld4_plain(x + idx + g.sy), dn = ld4_plain(x + idx - g.sy);
+    const float left = pos.first_x ? 0.f : x[idx - 1], right = pos.last_x ? 0.f : x[idx + 4];
+    float4 zu = make_float4(0.f, 0.f, 0.f, 0.f), zd = zu;
+    if (HZ) { zu = ld4_plain(x + idx + g.sz); zd = ld4_plain(x + idx - g.sz); }
+    const float4 r4 = ld4_stream(rhs + idx);
+    const uint32_t fl = flags ? ld_flags4(flags + idx) : 0u;
+    const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
+    const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+    const float zuv[4] = {zu.x, zu.y, zu.z, zu.w}, zdv[4] = {zd.x, zd.y, zd.z, zd.w};
+    const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
+    const FsDivisor dv = fs_make_divisor(c);
+    const int par = (j + kl + g.zoff) & 1; // x0 is a multiple of 4: lane l has colour (l + j + k) & 1
+    float v[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+        float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
+        if (HZ) s = (s + zuv[l]) + zdv[l];
+        const float val = fs_div(rv[l] + a * s, dv);
+        const bool ring_lane = (l == 0 && pos.first_x) || (l == 3 && pos.last_x);
+        const bool upd = (((l + par) & 1) == colour) && !((fl >> (8 * l)) & 1u) && !ring_lane;
+        v[l] = upd ? val : cv[l + 1];
+    }
+    if (write_ring) {
+        fs_vec4_store_ring(x, g, pos, v, b);
+    } else {
+        st4(x + idx, v);
+    }
+}
+
 // ---- metrics (LogCurrentMetrics, FluidSim.cs:582-594): sum of density, max |V| -------------------------
 __global__ void __launch_bounds__(256)
 metrics_kernel(const float *__restrict__ d, const float *__restrict__ ux, const float *__restrict__ uy,

@@ -60,10 +60,11 @@ struct HostExec {
             cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         if (fuse_halo) halo(g, out);
     }
-    void rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour) {
+    bool rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour, int /*b*/) {
         cells(g, [&](int i, int j, int kl) {
             if (((i + j + kl + g.zoff) & 1) == colour) fs_rb_cell(g, x, rhs, flags, a, c, i, j, kl);
         });
+        return false;
     }
     void bnd(const FsGrid &g, float *x, int b) {
         cells(g, [&](int i, int j, int kl) { fs_bnd_cell(g, x, b, i, j, kl); });
