@@ -26,6 +26,10 @@ struct CudaExec {
     int dev = 0;
     cudaStream_t st = nullptr;
     cudaStream_t st_halo = nullptr;                  // side stream: the halo push runs beside the interior launch
+    cudaStream_t st_copy = nullptr;                  // copy stream: pipelined device->host readback (fs_get_field_async)
+    float *stage[FS_FIELD_COUNT] = {};               // per-field device snapshots the copy stream reads from
+    size_t stage_bytes[FS_FIELD_COUNT] = {};
+    cudaEvent_t ev_snap[FS_FIELD_COUNT] = {}, ev_sent[FS_FIELD_COUNT] = {};
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool bad = false;
@@ -81,6 +85,7 @@ struct CudaExec {
         FS_CUDA(cudaSetDevice(dev));
         FS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         FS_CUDA(cudaStreamCreateWithFlags(&st_halo, cudaStreamNonBlocking));
+        FS_CUDA(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         FS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreate(&ev0));
@@ -104,6 +109,14 @@ struct CudaExec {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
+        for (int f = 0; f < FS_FIELD_COUNT; f++) {
+            if (stage[f]) cudaFree(stage[f]);
+            if (ev_snap[f]) cudaEventDestroy(ev_snap[f]);
+            if (ev_sent[f]) cudaEventDestroy(ev_sent[f]);
+            stage[f] = nullptr; ev_snap[f] = ev_sent[f] = nullptr; stage_bytes[f] = 0;
+        }
+        st_copy = nullptr;
         if (st_halo) cudaStreamDestroy(st_halo);
         if (st) cudaStreamDestroy(st);
         d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = ev_fork = ev_join = nullptr; st = st_halo = nullptr;
@@ -127,6 +140,28 @@ struct CudaExec {
         FS_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
         FS_CUDA(cudaStreamSynchronize(st));
     }
+    // Pipelined readback: snapshot the field on the compute stream (device->device, ~0.2 ms per 512 MB), then copy
+    // the snapshot to the host on the copy stream while the next step computes.  `slot` = field id.
+    void download_async(void *dst, const void *src, size_t bytes, int slot) {
+        if (stage_bytes[slot] < bytes) {
+            if (stage[slot]) { cudaStreamSynchronize(st_copy); cudaFree(stage[slot]); }
+            stage[slot] = (float *)alloc(bytes);
+            stage_bytes[slot] = stage[slot] ? bytes : 0;
+            if (!stage[slot]) return;
+        }
+        if (!ev_snap[slot]) {
+            FS_CUDA(cudaEventCreateWithFlags(&ev_snap[slot], cudaEventDisableTiming));
+            FS_CUDA(cudaEventCreateWithFlags(&ev_sent[slot], cudaEventDisableTiming));
+        } else {
+            FS_CUDA(cudaStreamWaitEvent(st, ev_sent[slot], 0)); // the previous transfer out of this snapshot is done
+        }
+        FS_CUDA(cudaMemcpyAsync(stage[slot], src, bytes, cudaMemcpyDeviceToDevice, st));
+        FS_CUDA(cudaEventRecord(ev_snap[slot], st));
+        FS_CUDA(cudaStreamWaitEvent(st_copy, ev_snap[slot], 0));
+        FS_CUDA(cudaMemcpyAsync(dst, stage[slot], bytes, cudaMemcpyDeviceToHost, st_copy));
+        FS_CUDA(cudaEventRecord(ev_sent[slot], st_copy));
+    }
+    void wait_transfers() { FS_CUDA(cudaStreamSynchronize(st_copy)); }
     void sync() {
         FS_CUDA(cudaStreamSynchronize(st));
         if (halo_on && my_flags) {

@@ -88,6 +88,10 @@ int fs_get_field(fs_solver *s, int32_t field, float *out, int64_t n) { FS_GUARD(
 
 int fs_set_field(fs_solver *s, int32_t field, const float *in, int64_t n) { FS_GUARD(s); return c.set_field(field, in, n); }
 
+int fs_get_field_async(fs_solver *s, int32_t field, float *out, int64_t n) { FS_GUARD(s); return c.get_field_async(field, out, n); }
+
+int fs_wait_transfers(fs_solver *s) { FS_GUARD(s); c.ex.wait_transfers(); return c.check(); }
+
 int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density) {
     FS_GUARD(s);
     double sum = 0.0;

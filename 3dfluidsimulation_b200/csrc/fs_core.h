@@ -354,6 +354,13 @@ struct SolverCore {
         ex.download(out, p + g.sz * g.kb, sizeof(float) * nowned);
         return check();
     }
+    int get_field_async(int f, float *out, long long n) {
+        float *p = field_ptr(f);
+        if (!p) return fail(FS_ERR_BAD_ARGUMENT, "unknown or unallocated field");
+        if (!out || n != nowned) return fail(FS_ERR_BAD_ARGUMENT, "n must equal the owned voxel count");
+        ex.download_async(out, p + g.sz * g.kb, sizeof(float) * nowned, f);
+        return check();
+    }
     int set_field(int f, const float *in, long long n) {
         float *p = field_ptr(f);
         if (!p) return fail(FS_ERR_BAD_ARGUMENT, "unknown or unallocated field");

@@ -26,7 +26,7 @@ JACOBI, RED_BLACK = 0, 1
 EXPORTS = [
     "fs_abi_version", "fs_create", "fs_destroy", "fs_reset", "fs_last_error", "fs_slab_range",
     "fs_set_obstacles", "fs_add_density", "fs_add_velocity", "fs_add_source_cells", "fs_add_sources",
-    "fs_step", "fs_sync", "fs_get_field", "fs_set_field", "fs_get_metrics",
+    "fs_step", "fs_sync", "fs_get_field", "fs_set_field", "fs_get_field_async", "fs_wait_transfers", "fs_get_metrics",
     "fs_op_set_bnd", "fs_op_diffuse", "fs_op_smooth", "fs_op_lin_solve", "fs_op_project", "fs_op_advect",
     "fs_op_advect_velocity", "fs_op_enforce_obstacles",
     "fs_timer_start", "fs_timer_stop", "fs_launch_count", "fs_bench_sweep",
@@ -81,6 +81,8 @@ def load(path: str | None = None) -> C.CDLL:
         "fs_sync": (C.c_int, [vp]),
         "fs_get_field": (C.c_int, [vp, i32, vp, i64]),
         "fs_set_field": (C.c_int, [vp, i32, vp, i64]),
+        "fs_get_field_async": (C.c_int, [vp, i32, vp, i64]),
+        "fs_wait_transfers": (C.c_int, [vp]),
         "fs_get_metrics": (C.c_int, [vp, _F, _F, C.POINTER(C.c_double)]),
         "fs_op_set_bnd": (C.c_int, [vp, i32, i32]),
         "fs_op_diffuse": (C.c_int, [vp, i32, i32, i32, f32, f32]),
@@ -199,6 +201,14 @@ class NativeSolver:
             out = np.empty(self.shape, np.float32)
         self._ck(self.lib.fs_get_field(self.h, fid, _ptr(out, np.float32), out.size))
         return out
+
+    def get_field_async(self, field, out: np.ndarray):
+        """Pipelined readback into `out` (pinned for full speed); valid after wait_transfers()."""
+        fid = FIELD_IDS[field] if isinstance(field, str) else int(field)
+        self._ck(self.lib.fs_get_field_async(self.h, fid, _ptr(out, np.float32), out.size))
+
+    def wait_transfers(self):
+        self._ck(self.lib.fs_wait_transfers(self.h))
 
     def set_field(self, field, a: np.ndarray):
         fid = FIELD_IDS[field] if isinstance(field, str) else int(field)

@@ -70,6 +70,9 @@ namespace FluidSolverNative
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_sync(SolverHandle s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_field(SolverHandle s, int field, float[] dst, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_set_field(SolverHandle s, int field, float[] src, long n);
+        // pipelined readback: dst must be pinned (GCHandle.Alloc(..., GCHandleType.Pinned)) until fs_wait_transfers returns
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_field_async(SolverHandle s, int field, IntPtr dst, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_wait_transfers(SolverHandle s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_metrics(SolverHandle s, out float meanDensity, out float maxSpeed, out double sumDensity);
 
         // operator entry points (one reference job chain each); used by tests and by hosts that compose their own step

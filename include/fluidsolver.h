@@ -112,6 +112,12 @@ int fs_sync(fs_solver *s);
  * n must equal the handle's owned voxel count; planes are in global z order. */
 int fs_get_field(fs_solver *s, int32_t field, float *out, int64_t n);
 int fs_set_field(fs_solver *s, int32_t field, const float *in, int64_t n);
+/* Pipelined form of fs_get_field for per-frame readback (what Update() does after Simulate(), :443): the field is
+ * snapshotted in stream order and copied to `out` on a copy stream while later steps compute.  `out` must stay
+ * valid (pinned for full speed) and must not be read until fs_wait_transfers() returns.  One transfer per field id
+ * may be in flight; a second call for the same field waits for the first on the device, never on the host. */
+int fs_get_field_async(fs_solver *s, int32_t field, float *out, int64_t n);
+int fs_wait_transfers(fs_solver *s);
 
 /* ---- metrics: LogCurrentMetrics, FluidSim.cs:582-594 (mean density, max |V|) over owned voxels;
  * sum_density is returned so that slabs can be combined. */

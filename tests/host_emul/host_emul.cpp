@@ -35,6 +35,8 @@ struct HostExec {
     void copy(void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); }
     void upload(void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); }
     void download(void *d, const void *s, size_t bytes) { memcpy(d, s, bytes); }
+    void download_async(void *d, const void *s, size_t bytes, int) { memcpy(d, s, bytes); }
+    void wait_transfers() {}
     void sync() {}
 
     template <class F>

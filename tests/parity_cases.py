@@ -297,3 +297,25 @@ def case_golden_trajectory(lib, name, use_graph=False):
                         assert_close(s.get_field(k), g[f"step{step}_{k}"], 1e-6 * step, f"golden trajectory step {step} {k}")
                     else:
                         assert_exact(s.get_field(k), g[f"step{step}_{k}"], f"golden trajectory step {step} {k}")
+
+
+def case_async_readback(lib, nx=16, ny=12, nz=9):
+    """fs_get_field_async + fs_wait_transfers returns what fs_get_field returns, also when a step is enqueued
+    between the request and the wait (the snapshot is taken in stream order)."""
+    rng = np.random.default_rng(21)
+    shape = shape_of(nx, ny, nz)
+    with make_solver(lib, nx, ny, nz, iters_diffuse=3, iters_pressure=4, enable_obstacle=False) as s:
+        for n in ("density", "vx", "vy") + (("vz",) if nz > 1 else ()):
+            s.set_field(n, rnd(shape, rng))
+        s.step(0.05, 1e-3, 1e-3)
+        want_d, want_p = s.get_field("density"), s.get_field("pressure")
+        out_d, out_p = np.empty(shape, f32), np.empty(shape, f32)
+        s.get_field_async("density", out_d)
+        s.get_field_async("pressure", out_p)
+        s.step(0.05, 1e-3, 1e-3)            # must not disturb the snapshots
+        s.wait_transfers()
+        assert_exact(out_d, want_d, "async density")
+        assert_exact(out_p, want_p, "async pressure")
+        s.get_field_async("density", out_d)  # second use of the same slot
+        s.wait_transfers()
+        assert_exact(out_d, s.get_field("density"), "async density, second transfer")

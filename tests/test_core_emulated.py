@@ -77,6 +77,10 @@ def test_red_black_matches_oracle(emul_lib, oracle):
             P.assert_exact(s.get_field("vy0"), oracle.lin_solve(b, guess, rhs, 0.3, 2.8, mask, 4, red_black=True), f"rb b={b}")
 
 
+def test_async_readback(emul_lib):
+    P.case_async_readback(emul_lib)
+
+
 def test_abi_errors(emul_lib, pkg):
     """Error behaviour of the boundary: negative status + message, never an exception across the ABI."""
     import numpy as np

@@ -91,6 +91,11 @@ def test_scene_configs_2d(lib, oracle):
     P.case_steps(lib, oracle, 128, 128, 1, 3, obstacles=True)
 
 
+def test_async_readback(lib):
+    P.case_async_readback(lib)
+    P.case_async_readback(lib, 64, 40, 35)
+
+
 def test_red_black_matches_oracle(lib, oracle):
     rng = np.random.default_rng(9)
     shape = (10, 9, 12)
