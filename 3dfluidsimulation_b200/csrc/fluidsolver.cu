@@ -36,6 +36,7 @@ struct CudaExec {
     std::string msg;
     int64_t launches = 0;
     bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
+    int tune_zchunk = 0, tune_by = 0; // FS_ZCHUNK / FS_BLOCK_Y: override the sweep's z chunk length / CTA rows (experiments)
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
     bool use_graph = false;
@@ -95,6 +96,8 @@ struct CudaExec {
         FS_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
         const char *fg = getenv("FS_FORCE_GENERIC");
         force_generic = fg && fg[0] == '1';
+        if (const char *e = getenv("FS_ZCHUNK")) tune_zchunk = atoi(e);
+        if (const char *e = getenv("FS_BLOCK_Y")) tune_by = atoi(e);
         const char *la = getenv("FS_L2_AHEAD");
         if (la) l2_ahead = atoi(la);
         return bad ? 1 : 0;
@@ -220,7 +223,7 @@ struct CudaExec {
             const int threads = thread_planes >= (long long)sm_count * 256 * 16 ? 256 : 64;
             int bx = 32;
             while (bx / 2 >= groups && bx > 1) bx /= 2;
-            const int by = threads / bx;
+            const int by = tune_by > 0 ? tune_by : threads / bx; // FS_BLOCK_Y (experiments)
             const int gxn = (groups + bx - 1) / bx, gyn = (g.ny - 2 + by - 1) / by;
             const long long blocks_xy = (long long)gxn * gyn;
             // z chunk per CTA: short enough for >= ~4 waves of 4 resident CTAs/SM (tail effect), long enough
@@ -229,6 +232,7 @@ struct CudaExec {
             long long zchunk = (long long)cnt * blocks_xy / target;
             if (zchunk < 4) zchunk = 4;
             if (zchunk > 16) zchunk = 16;
+            if (tune_zchunk > 0) zchunk = tune_zchunk; // FS_ZCHUNK (experiments)
             if (zchunk > cnt) zchunk = cnt;
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
             const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
