@@ -195,7 +195,6 @@ struct CudaExec {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
-        flush_halo_wait();
         const dim3 block(64, 4, 1);
         const dim3 grid((g.nx - 2 + 63) / 64, (g.ny - 2 + 3) / 4, cnt);
         cells_kernel<<<grid, block, 0, st>>>(g, kl0, f);
@@ -204,7 +203,6 @@ struct CudaExec {
     template <class F>
     void linear(long long n, F f) {
         if (n <= 0) return;
-        flush_halo_wait();
         linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, f);
         launches++;
     }
@@ -244,7 +242,6 @@ struct CudaExec {
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
          else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
-            flush_halo_wait(); // slabs: the ghost planes this sweep reads must have arrived
             if (halo_on && fuse_halo && nchunks > 2) {
                 // fork: side stream = boundary chunks, then the P2P push; main stream = interior chunks; join
                 FS_CUDA(cudaEventRecord(ev_fork, st));
@@ -268,7 +265,7 @@ struct CudaExec {
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         else
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
-        if (fuse_halo) halo(g, out); // per-cell fallback has no fused exchange
+        if (fuse_halo) halo(g, out); // per-cell fallback: push after the whole sweep
     }
     // returns true when the launch also performed set_bnd (colour 1 of the float4 kernel)
     bool rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour, int b) {
@@ -314,7 +311,6 @@ struct CudaExec {
         dim3 grid, block;
         int kl0;
         if (vec4_geometry(g, &grid, &block, &kl0)) {
-            flush_halo_wait();
             if (g.hz) divergence_vec4<true><<<grid, block, 0, st>>>(g, div, ux, uy, uz, kl0);
             else divergence_vec4<false><<<grid, block, 0, st>>>(g, div, ux, uy, uz, kl0);
             launches++;
@@ -326,7 +322,6 @@ struct CudaExec {
         dim3 grid, block;
         int kl0;
         if (vec4_geometry(g, &grid, &block, &kl0)) {
-            flush_halo_wait();
             if (g.hz) gradient_vec4<true><<<grid, block, 0, st>>>(g, ux, uy, uz, p, flags, kl0);
             else gradient_vec4<false><<<grid, block, 0, st>>>(g, ux, uy, uz, p, flags, kl0);
             launches++;
@@ -463,7 +458,6 @@ struct CudaExec {
     }
     FsHaloArgs halo_args(const FsGrid &g, const float *field, unsigned op_offset) const {
         FsHaloArgs h{};
-        h.enabled = halo_on ? 1 : 0;
         if (!halo_on) return h;
         const int bi = field ? buf_index(field) : -1;
         h.my_flags = my_flags;
@@ -480,7 +474,6 @@ struct CudaExec {
     }
     // Every halo_push_kernel retires only after the neighbours' planes of the same op have landed, so kernels
     // ordered after it can read the ghost planes without any further wait.
-    void flush_halo_wait() {}
     void halo(const FsGrid &g, float *field) { halo_on_stream(g, field, st); }
     void halo_on_stream(const FsGrid &g, float *field, cudaStream_t stream) {
         if (!halo_on) return;
@@ -498,11 +491,9 @@ struct CudaExec {
     void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
         if (!halo_on) return;
         halo(FsGrid{}, nullptr);
-        flush_halo_wait();
     }
     void halo_commit() {
         if (!halo_on || !ops_since_commit) return;
-        flush_halo_wait();
         halo_commit_kernel<<<1, 1, 0, st>>>(my_flags, ops_since_commit);
         launches++;
         ops_since_commit = 0;

@@ -194,7 +194,7 @@ struct SolverCore {
         if (b != 0 && n_obst && (b != 3 || g.hz)) ex.mirror(g, x, flags, obst_list, n_obst, b);
     }
     // One relaxation sweep + its boundary work.  Single slab: sweep, obstacle mirroring.  Several slabs: the
-    // sweep pushes its boundary planes into the neighbours' ghosts itself (fused halo) unless obstacle
+    // executor overlaps the push of the boundary planes with the interior of the same sweep (fuse_halo) unless obstacle
     // mirroring has to run on the boundary planes first (b != 0 with obstacles): then the order is
     // sweep, [halo when the mirror reads z neighbours], mirror, halo.
     void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,

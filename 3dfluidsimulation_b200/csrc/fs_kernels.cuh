@@ -132,7 +132,6 @@ struct FsHaloArgs {
     unsigned *lo_flags;     // neighbours' flag blocks (peer memory)
     unsigned *hi_flags;
     unsigned op_offset;
-    int enabled;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
