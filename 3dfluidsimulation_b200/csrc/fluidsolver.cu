@@ -108,6 +108,8 @@ struct CudaExec {
         if (d_sum) cudaFree(d_sum);
         if (d_max) cudaFree(d_max);
         if (scratch) cudaFree(scratch);
+        if (render_buf) cudaFree(render_buf);
+        render_buf = nullptr; render_bytes = 0;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -360,6 +362,23 @@ struct CudaExec {
     }
     void enforce(const FsGrid &g, float *ux, float *uy, float *uz, const uint8_t *flags, float cell, float rawvisc) {
         cells(g, [=] __device__(int i, int j, int kl) { fs_enforce_cell(g, ux, uy, uz, flags, cell, rawvisc, i, j, kl); });
+    }
+    float *render_buf = nullptr;
+    size_t render_bytes = 0;
+    void *render_buffer(size_t bytes) {
+        if (bytes > render_bytes) {
+            if (render_buf) { cudaStreamSynchronize(st); cudaFree(render_buf); }
+            render_buf = (float *)alloc(bytes);
+            render_bytes = render_buf ? bytes : 0;
+        }
+        return render_buf;
+    }
+    void visualize(const FsGrid &g, const fs_vis_params &vp, const float *d, const float *p, const uint8_t *mask, float *rgba) {
+        const int nx = g.nx;
+        linear(g.sz, [=] __device__(long long t) {
+            const FsColor c = fs_visualize_cell(vp, d[t], p[t], mask[t] != 0, (int)(t % nx), (int)(t / nx));
+            reinterpret_cast<float4 *>(rgba)[t] = make_float4(c.r, c.g, c.b, c.a);
+        });
     }
     void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
         const long long n = g.sz * g.nzl;

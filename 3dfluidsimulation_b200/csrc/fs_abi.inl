@@ -92,6 +92,8 @@ int fs_get_field_async(fs_solver *s, int32_t field, float *out, int64_t n) { FS_
 
 int fs_wait_transfers(fs_solver *s) { FS_GUARD(s); c.ex.wait_transfers(); return c.check(); }
 
+int fs_render_rgba(fs_solver *s, const fs_vis_params *vp, float *out_rgba, int64_t n) { FS_GUARD(s); return c.render(vp, out_rgba, n); }
+
 int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density) {
     FS_GUARD(s);
     double sum = 0.0;

@@ -13,6 +13,8 @@
 #pragma once
 #include <stdint.h>
 
+#include "../../include/fluidsolver.h"
+
 #if defined(__CUDACC__)
 #define FS_HD __host__ __device__ __forceinline__
 #else
@@ -347,4 +349,69 @@ FS_HD uint8_t fs_flags_cell(const FsGrid &g, const uint8_t *mask, int i, int j, 
     if (kl > 0 && mask[idx - g.sz]) f |= FS_OB_ZM;
     if (kl < g.nzl - 1 && mask[idx + g.sz]) f |= FS_OB_ZP;
     return f;
+}
+
+// ---- visualisation colour mapping (next row N2) ------------------------------------------------------------------
+// UpdateVisualizationJob.Execute, FluidSim.cs:1888-1979, for one cell of one xy plane.  Color.Lerp clamps t to
+// [0,1]; Color.black = (0,0,0,1); the "very high pressure" colour is (1, 0.5, 0, 1) (:1962).
+struct FsColor { float r, g, b, a; };
+FS_HD FsColor fs_color4(const float *c) { FsColor o = {c[0], c[1], c[2], c[3]}; return o; }
+FS_HD FsColor fs_color_lerp(FsColor a, FsColor b, float t) {
+    t = t < 0.0f ? 0.0f : (t > 1.0f ? 1.0f : t);
+    FsColor o = {a.r + (b.r - a.r) * t, a.g + (b.g - a.g) * t, a.b + (b.b - a.b) * t, a.a + (b.a - a.a) * t};
+    return o;
+}
+FS_HD FsColor fs_eval_gradient(const fs_vis_params &vp, float time) { // :1981-2001
+    const int n = vp.gradient_key_count;
+    if (n <= 0) { FsColor w = {1.0f, 1.0f, 1.0f, 1.0f}; return w; }
+    if (time <= vp.gradient_times[0]) return fs_color4(vp.gradient_colors[0]);
+    if (time >= vp.gradient_times[n - 1]) return fs_color4(vp.gradient_colors[n - 1]);
+    int index = 0;
+    while (index < n - 1 && time > vp.gradient_times[index + 1]) index++;
+    const float t = (time - vp.gradient_times[index]) / (vp.gradient_times[index + 1] - vp.gradient_times[index]);
+    return fs_color_lerp(fs_color4(vp.gradient_colors[index]), fs_color4(vp.gradient_colors[index + 1]), t);
+}
+FS_HD FsColor fs_visualize_cell(const fs_vis_params &vp, float d, float p, bool obstacle, int i, int j) {
+    if (obstacle) return fs_color4(vp.obstacle_color); // :1894-1899
+    const float normalizedD = d * vp.colour_intensity;
+    FsColor px;
+    if (vp.color_mode == 2) { // DensityBased :1908-1928
+        if (d < vp.medium_density_threshold) {
+            const FsColor black = {0.0f, 0.0f, 0.0f, 1.0f};
+            px = fs_color_lerp(black, fs_color4(vp.low_density_color), d / vp.medium_density_threshold);
+        } else if (d < vp.high_density_threshold) {
+            const float t = (d - vp.medium_density_threshold) / (vp.high_density_threshold - vp.medium_density_threshold);
+            px = fs_color_lerp(fs_color4(vp.low_density_color), fs_color4(vp.medium_density_color), t);
+        } else {
+            float t = (d - vp.high_density_threshold) / vp.high_density_threshold;
+            t = t < 1.0f ? t : 1.0f;
+            px = fs_color_lerp(fs_color4(vp.medium_density_color), fs_color4(vp.high_density_color), t);
+        }
+    } else if (vp.color_mode == 1) { // Gradient :1930-1934
+        const float c = normalizedD < 0.0f ? 0.0f : (normalizedD > 1.0f ? 1.0f : normalizedD);
+        px = fs_eval_gradient(vp, c);
+    } else if (vp.color_mode == 3) { // PressureBased :1947-1964
+        if (p < vp.low_pressure_threshold) {
+            const float t = p / vp.low_pressure_threshold;
+            px = fs_color_lerp(fs_color4(vp.low_pressure_color), fs_color4(vp.neutral_pressure_color), 1.0f + t);
+        } else if (p <= vp.high_pressure_threshold) {
+            const float t = (p - vp.low_pressure_threshold) / (vp.high_pressure_threshold - vp.low_pressure_threshold);
+            px = fs_color_lerp(fs_color4(vp.neutral_pressure_color), fs_color4(vp.high_pressure_color), t);
+        } else {
+            float t = (p - vp.high_pressure_threshold) / vp.high_pressure_threshold;
+            t = t < 1.0f ? t : 1.0f;
+            const FsColor orange = {1.0f, 0.5f, 0.0f, 1.0f};
+            px = fs_color_lerp(fs_color4(vp.high_pressure_color), orange, t);
+        }
+    } else { // SingleColor and default (Streamlines) :1936-1945
+        const FsColor c = {vp.fluid_color[0] * normalizedD, vp.fluid_color[1] * normalizedD, vp.fluid_color[2] * normalizedD,
+                           vp.fluid_color[3]};
+        px = c;
+    }
+    if (vp.visualize_source_position && vp.enable_custom_source) { // :1970-1978
+        const float dx = (float)i - vp.source_x, dy = (float)j - vp.source_y;
+        const float distSq = dx * dx + dy * dy;
+        if (distSq < vp.visual_marker_radius * vp.visual_marker_radius) px = fs_color4(vp.source_position_color);
+    }
+    return px;
 }

@@ -318,6 +318,22 @@ struct SolverCore {
         return check();
     }
 
+    // ---- visualisation (next row N2) -----------------------------------------------------------------------
+    int render(const fs_vis_params *vp, float *out, long long n) {
+        if (!vp || !out || n != g.sy * g.ny * 4) return fail(FS_ERR_BAD_ARGUMENT, "out_rgba must hold nx*ny*4 floats");
+        if (vp->gradient_key_count < 0 || vp->gradient_key_count > 8) return fail(FS_ERR_BAD_ARGUMENT, "gradient_key_count must be 0..8");
+        int kl = 0;
+        if (g.hz) {
+            if (vp->z_slice < zb || vp->z_slice >= ze) return fail(FS_ERR_BAD_ARGUMENT, "z_slice is not owned by this handle");
+            kl = vp->z_slice - g.zoff;
+        }
+        float *dev = (float *)ex.render_buffer(sizeof(float) * (size_t)n);
+        if (!dev) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
+        ex.visualize(g, *vp, density + g.sz * kl, pressure + g.sz * kl, mask + g.sz * kl, dev);
+        ex.download(out, dev, sizeof(float) * (size_t)n);
+        return check();
+    }
+
     // ---- field access -----------------------------------------------------------------------------
     float *field_ptr(int f) {
         switch (f) {

@@ -44,6 +44,40 @@ class FsParams(C.Structure):
     ]
 
 
+class FsVisParams(C.Structure):
+    """fs_vis_params (include/fluidsolver.h): parameters of the reference's UpdateVisualizationJob."""
+    _fields_ = [
+        ("color_mode", C.c_int32), ("visualize_source_position", C.c_int32), ("enable_custom_source", C.c_int32),
+        ("gradient_key_count", C.c_int32), ("z_slice", C.c_int32),
+        ("source_x", C.c_float), ("source_y", C.c_float), ("visual_marker_radius", C.c_float),
+        ("colour_intensity", C.c_float),
+        ("medium_density_threshold", C.c_float), ("high_density_threshold", C.c_float),
+        ("low_pressure_threshold", C.c_float), ("high_pressure_threshold", C.c_float),
+        ("fluid_color", C.c_float * 4), ("obstacle_color", C.c_float * 4), ("source_position_color", C.c_float * 4),
+        ("low_density_color", C.c_float * 4), ("medium_density_color", C.c_float * 4), ("high_density_color", C.c_float * 4),
+        ("low_pressure_color", C.c_float * 4), ("neutral_pressure_color", C.c_float * 4), ("high_pressure_color", C.c_float * 4),
+        ("gradient_colors", (C.c_float * 4) * 8), ("gradient_times", C.c_float * 8),
+    ]
+
+    @classmethod
+    def reference_defaults(cls, size, mode=0):
+        """The inspector defaults of FluidSim.cs:57-83 (Unity's Color constants spelled out)."""
+        v = cls()
+        v.color_mode, v.visualize_source_position, v.enable_custom_source = mode, 1, 0
+        v.source_x, v.source_y, v.visual_marker_radius = 0.5 * size, 0.5 * size, 3.0
+        v.colour_intensity = 1.0
+        v.medium_density_threshold, v.high_density_threshold = 50.0, 200.0
+        v.low_pressure_threshold, v.high_pressure_threshold = -50.0, 50.0
+        white, blue, green, red, gray, yellow = (1, 1, 1, 1), (0, 0, 1, 1), (0, 1, 0, 1), (1, 0, 0, 1), (0.5, 0.5, 0.5, 1), (1, 0.92156863, 0.01568628, 1)
+        v.fluid_color[:], v.obstacle_color[:], v.source_position_color[:] = white, gray, yellow
+        v.low_density_color[:], v.medium_density_color[:], v.high_density_color[:] = blue, green, red
+        v.low_pressure_color[:], v.neutral_pressure_color[:], v.high_pressure_color[:] = blue, white, red
+        v.gradient_key_count = 2                      # Start(): blue at 0, red at 1 (:188-203)
+        v.gradient_colors[0][:], v.gradient_colors[1][:] = blue, red
+        v.gradient_times[0], v.gradient_times[1] = 0.0, 1.0
+        return v
+
+
 class FluidSolverError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"fluidsolver error {code}: {message}")
@@ -84,6 +118,7 @@ def load(path: str | None = None) -> C.CDLL:
         "fs_get_field_async": (C.c_int, [vp, i32, vp, i64]),
         "fs_wait_transfers": (C.c_int, [vp]),
         "fs_get_metrics": (C.c_int, [vp, _F, _F, C.POINTER(C.c_double)]),
+        "fs_render_rgba": (C.c_int, [vp, C.POINTER(FsVisParams), vp, i64]),
         "fs_op_set_bnd": (C.c_int, [vp, i32, i32]),
         "fs_op_diffuse": (C.c_int, [vp, i32, i32, i32, f32, f32]),
         "fs_op_smooth": (C.c_int, [vp, i32, i32, i32, f32, f32, i32]),
@@ -214,6 +249,13 @@ class NativeSolver:
         fid = FIELD_IDS[field] if isinstance(field, str) else int(field)
         a = np.ascontiguousarray(a, dtype=np.float32)
         self._ck(self.lib.fs_set_field(self.h, fid, a.ctypes.data, a.size))
+
+    def render_rgba(self, vis: "FsVisParams", out: np.ndarray | None = None) -> np.ndarray:
+        """UpdateVisualizationJob on the device: (ny, nx, 4) float32 RGBA of one xy plane."""
+        if out is None:
+            out = np.empty((self.ny, self.nx, 4), np.float32)
+        self._ck(self.lib.fs_render_rgba(self.h, C.byref(vis), _ptr(out, np.float32), out.size))
+        return out
 
     def metrics(self):
         m, s, t = C.c_float(), C.c_float(), C.c_double()

@@ -12,6 +12,7 @@
 //   * the solver handle is an opaque IntPtr wrapped in a SafeHandle so that a domain reload frees the GPU memory.
 using System;
 using System.Runtime.InteropServices;
+using UnityEngine;
 
 namespace FluidSolverNative
 {
@@ -73,6 +74,8 @@ namespace FluidSolverNative
         // pipelined readback: dst must be pinned (GCHandle.Alloc(..., GCHandleType.Pinned)) until fs_wait_transfers returns
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_field_async(SolverHandle s, int field, IntPtr dst, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_wait_transfers(SolverHandle s);
+        // device-side UpdateVisualizationJob: one xy plane as RGBA floats (Color[] layout); vp = fs_vis_params blob (see include/fluidsolver.h)
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_render_rgba(SolverHandle s, IntPtr visParams, [Out] Color[] outRgba, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_metrics(SolverHandle s, out float meanDensity, out float maxSpeed, out double sumDensity);
 
         // operator entry points (one reference job chain each); used by tests and by hosts that compose their own step

@@ -119,6 +119,30 @@ int fs_set_field(fs_solver *s, int32_t field, const float *in, int64_t n);
 int fs_get_field_async(fs_solver *s, int32_t field, float *out, int64_t n);
 int fs_wait_transfers(fs_solver *s);
 
+/* ---- visualisation colour mapping: UpdateVisualizationJob, FluidSim.cs:1851-2002,
+ * with the parameters UpdateVisualization passes (:799-829).  Renders one xy plane (the whole grid when nz == 1,
+ * plane z_slice otherwise) to RGBA floats in the reference's Color[] layout, on the device, so that a frame needs
+ * nx*ny*16 bytes of readback instead of the density and pressure fields.  colour arrays are r,g,b,a. */
+typedef struct fs_vis_params {
+    int32_t color_mode;                /* ColorMode :32: 0 SingleColor, 1 Gradient, 2 DensityBased, 3 PressureBased, 4 Streamlines */
+    int32_t visualize_source_position; /* :54 */
+    int32_t enable_custom_source;      /* :35 */
+    int32_t gradient_key_count;        /* 0..8 */
+    int32_t z_slice;                   /* global z plane to render (ignored when nz == 1); must be owned by this handle */
+    float source_x, source_y;          /* sourcePosition * currentSize :805-806 */
+    float visual_marker_radius;        /* 3 in the reference :807 */
+    float colour_intensity;
+    float medium_density_threshold, high_density_threshold;
+    float low_pressure_threshold, high_pressure_threshold;
+    float fluid_color[4], obstacle_color[4], source_position_color[4];
+    float low_density_color[4], medium_density_color[4], high_density_color[4];
+    float low_pressure_color[4], neutral_pressure_color[4], high_pressure_color[4];
+    float gradient_colors[8][4];
+    float gradient_times[8];
+} fs_vis_params;
+/* out_rgba: nx*ny*4 floats, n = nx*ny*4. */
+int fs_render_rgba(fs_solver *s, const fs_vis_params *vp, float *out_rgba, int64_t n);
+
 /* ---- metrics: LogCurrentMetrics, FluidSim.cs:582-594 (mean density, max |V|) over owned voxels;
  * sum_density is returned so that slabs can be combined. */
 int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density);

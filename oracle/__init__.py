@@ -154,6 +154,14 @@ def enforce_obstacles(vx, vy, vz, obs, cell, rawvisc):
     return vx, vy, vz
 
 
+def visualize(density, pressure, obstacles, vis):
+    """fo_visualize on one (ny, nx) plane; `vis` is any ctypes struct with fs_vis_params' layout."""
+    ny, nx = density.shape
+    out = np.empty((ny, nx, 4), np.float32)
+    lib().fo_visualize(nx, ny, _f(density), _f(pressure), _u(obstacles), C.byref(vis), out.ctypes.data_as(_F))
+    return out
+
+
 def cell_index(shape, x, y, z=0.0):
     nx, ny, nz = _dims(shape)
     return int(lib().fo_cell_index(nx, ny, nz, _cf(x), _cf(y), _cf(z)))

@@ -408,3 +408,82 @@ void fo_metrics(const fo_state *s, float *mean_density, float *max_speed) {
     *mean_density = (float)(acc / (double)total);
     *max_speed = mx;
 }
+
+/* ---- visualisation colour mapping: UpdateVisualizationJob.Execute, FluidSim.cs:1888-2001 (next row N2) ----------
+ * One xy plane of size nx*ny; out is nx*ny Color (r,g,b,a floats), as the reference's NativeArray<Color>. */
+typedef struct { float r, g, b, a; } fo_color;
+static fo_color fo_c4(const float *c) { fo_color o = {c[0], c[1], c[2], c[3]}; return o; }
+static fo_color fo_lerp(fo_color a, fo_color b, float t) { /* Color.Lerp: t clamped to [0,1] */
+    if (t < 0.0f) t = 0.0f;
+    if (t > 1.0f) t = 1.0f;
+    fo_color o = {a.r + (b.r - a.r) * t, a.g + (b.g - a.g) * t, a.b + (b.b - a.b) * t, a.a + (b.a - a.a) * t};
+    return o;
+}
+static fo_color fo_gradient(const fo_vis_params *vp, float time) { /* EvaluateGradient :1981-2001 */
+    const int n = vp->gradient_key_count;
+    if (n <= 0) { fo_color w = {1, 1, 1, 1}; return w; }
+    if (time <= vp->gradient_times[0]) return fo_c4(vp->gradient_colors[0]);
+    if (time >= vp->gradient_times[n - 1]) return fo_c4(vp->gradient_colors[n - 1]);
+    int index = 0;
+    while (index < n - 1 && time > vp->gradient_times[index + 1]) index++;
+    float t = (time - vp->gradient_times[index]) / (vp->gradient_times[index + 1] - vp->gradient_times[index]);
+    return fo_lerp(fo_c4(vp->gradient_colors[index]), fo_c4(vp->gradient_colors[index + 1]), t);
+}
+void fo_visualize(int nx, int ny, const float *density, const float *pressure, const uint8_t *obstacles,
+                  const fo_vis_params *vp, float *out) {
+    for (int index = 0; index < nx * ny; index++) {
+        const int i = index % nx, j = index / nx;
+        fo_color px;
+        if (obstacles[index]) { px = fo_c4(vp->obstacle_color); goto store; } /* :1894-1899 */
+        {
+            const float d = density[index];
+            const float normalizedD = d * vp->colour_intensity;
+            switch (vp->color_mode) {
+            case 2: /* DensityBased */
+                if (d < vp->medium_density_threshold) {
+                    fo_color black = {0, 0, 0, 1};
+                    px = fo_lerp(black, fo_c4(vp->low_density_color), d / vp->medium_density_threshold);
+                } else if (d < vp->high_density_threshold) {
+                    float t = (d - vp->medium_density_threshold) / (vp->high_density_threshold - vp->medium_density_threshold);
+                    px = fo_lerp(fo_c4(vp->low_density_color), fo_c4(vp->medium_density_color), t);
+                } else {
+                    float t = fminf(1.0f, (d - vp->high_density_threshold) / vp->high_density_threshold);
+                    px = fo_lerp(fo_c4(vp->medium_density_color), fo_c4(vp->high_density_color), t);
+                }
+                break;
+            case 1: { /* Gradient */
+                float c = normalizedD < 0.0f ? 0.0f : (normalizedD > 1.0f ? 1.0f : normalizedD);
+                px = fo_gradient(vp, c);
+                break;
+            }
+            case 3: { /* PressureBased */
+                const float p = pressure[index];
+                if (p < vp->low_pressure_threshold) {
+                    float t = p / vp->low_pressure_threshold;
+                    px = fo_lerp(fo_c4(vp->low_pressure_color), fo_c4(vp->neutral_pressure_color), 1.0f + t);
+                } else if (p <= vp->high_pressure_threshold) {
+                    float t = (p - vp->low_pressure_threshold) / (vp->high_pressure_threshold - vp->low_pressure_threshold);
+                    px = fo_lerp(fo_c4(vp->neutral_pressure_color), fo_c4(vp->high_pressure_color), t);
+                } else {
+                    float t = fminf(1.0f, (p - vp->high_pressure_threshold) / vp->high_pressure_threshold);
+                    fo_color orange = {1.0f, 0.5f, 0.0f, 1.0f};
+                    px = fo_lerp(fo_c4(vp->high_pressure_color), orange, t);
+                }
+                break;
+            }
+            default: /* SingleColor, Streamlines */
+                px.r = vp->fluid_color[0] * normalizedD;
+                px.g = vp->fluid_color[1] * normalizedD;
+                px.b = vp->fluid_color[2] * normalizedD;
+                px.a = vp->fluid_color[3];
+                break;
+            }
+            if (vp->visualize_source_position && vp->enable_custom_source) { /* :1970-1978 */
+                float distSq = (i - vp->source_x) * (i - vp->source_x) + (j - vp->source_y) * (j - vp->source_y);
+                if (distSq < vp->visual_marker_radius * vp->visual_marker_radius) px = fo_c4(vp->source_position_color);
+            }
+        }
+    store:
+        out[4 * index] = px.r; out[4 * index + 1] = px.g; out[4 * index + 2] = px.b; out[4 * index + 3] = px.a;
+    }
+}

@@ -20,6 +20,20 @@ typedef struct fo_state {
     const uint8_t *obstacles;                                   /* 1 byte per cell */
 } fo_state;
 
+/* parameters of UpdateVisualizationJob (FluidSim.cs:1859-1886, :799-829); same field order as fs_vis_params */
+typedef struct fo_vis_params {
+    int32_t color_mode, visualize_source_position, enable_custom_source, gradient_key_count, z_slice;
+    float source_x, source_y, visual_marker_radius, colour_intensity;
+    float medium_density_threshold, high_density_threshold, low_pressure_threshold, high_pressure_threshold;
+    float fluid_color[4], obstacle_color[4], source_position_color[4];
+    float low_density_color[4], medium_density_color[4], high_density_color[4];
+    float low_pressure_color[4], neutral_pressure_color[4], high_pressure_color[4];
+    float gradient_colors[8][4];
+    float gradient_times[8];
+} fo_vis_params;
+void fo_visualize(int nx, int ny, const float *density, const float *pressure, const uint8_t *obstacles,
+                  const fo_vis_params *vp, float *out);
+
 void fo_set_bnd(int nx, int ny, int nz, int b, float *x, const uint8_t *obs);
 void fo_diffuse_coeffs(int n, float diff, float dt, float *a, float *c);
 void fo_diffuse_smooth(int nx, int ny, int nz, int b, float *x, const float *x0, float a, float c,

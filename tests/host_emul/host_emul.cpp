@@ -100,6 +100,14 @@ struct HostExec {
     void enforce(const FsGrid &g, float *ux, float *uy, float *uz, const uint8_t *flags, float cell, float rawvisc) {
         cells(g, [&](int i, int j, int kl) { fs_enforce_cell(g, ux, uy, uz, flags, cell, rawvisc, i, j, kl); });
     }
+    std::vector<float> render_buf;
+    void *render_buffer(size_t bytes) { render_buf.resize(bytes / sizeof(float)); return render_buf.data(); }
+    void visualize(const FsGrid &g, const fs_vis_params &vp, const float *d, const float *p, const uint8_t *mask, float *rgba) {
+        for (long long t = 0; t < g.sz; t++) {
+            const FsColor c = fs_visualize_cell(vp, d[t], p[t], mask[t] != 0, (int)(t % g.nx), (int)(t / g.nx));
+            rgba[4 * t] = c.r; rgba[4 * t + 1] = c.g; rgba[4 * t + 2] = c.b; rgba[4 * t + 3] = c.a;
+        }
+    }
     void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
         for (int kl = 0; kl < g.nzl; kl++)
             for (int j = 0; j < g.ny; j++)

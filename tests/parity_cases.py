@@ -319,3 +319,42 @@ def case_async_readback(lib, nx=16, ny=12, nz=9):
         s.get_field_async("density", out_d)  # second use of the same slot
         s.wait_transfers()
         assert_exact(out_d, s.get_field("density"), "async density, second transfer")
+
+
+def case_visualize(lib, O, nx=24, ny=20, nz=1):
+    """fs_render_rgba (UpdateVisualizationJob on the device) vs the oracle's restatement, every colour mode,
+    obstacles, source marker, 2D and a 3D slice.  Bit exact (mul/add/div only)."""
+    rng = np.random.default_rng(31)
+    shape = shape_of(nx, ny, nz)
+    V = pkg().native.FsVisParams
+    with make_solver(lib, nx, ny, nz) as s:
+        d = (rng.random(shape, dtype=f32) * f32(300)).astype(f32)
+        p = ((rng.random(shape, dtype=f32) - f32(0.5)) * f32(250)).astype(f32)
+        m = (rng.random(shape) < 0.1).astype(np.uint8)
+        s.set_obstacles(m); s.set_field("density", d); s.set_field("pressure", p)
+        for mode in range(5):
+            for marker in (0, 1):
+                v = V.reference_defaults(nx, mode)
+                v.enable_custom_source = marker
+                v.source_x, v.source_y = 0.3 * nx, 0.6 * ny
+                v.colour_intensity = 0.004
+                if mode == 1:   # three gradient keys, unevenly spaced
+                    v.gradient_key_count = 3
+                    v.gradient_colors[1][:] = (0.2, 0.9, 0.1, 0.5)
+                    v.gradient_colors[2][:] = (1.0, 0.0, 0.0, 1.0)
+                    v.gradient_times[1], v.gradient_times[2] = 0.35, 1.0
+                k = 0
+                if nz > 1:
+                    k = nz // 2
+                    v.z_slice = k
+                got = s.render_rgba(v)
+                want = O.visualize(d[k] if nz > 1 else d, p[k] if nz > 1 else p, m[k] if nz > 1 else m, v)
+                assert_exact(got, want, f"visualize mode={mode} marker={marker} nz={nz}")
+        if nz > 1:
+            v = V.reference_defaults(nx, 0)
+            v.z_slice = nz + 3
+            try:
+                s.render_rgba(v)
+                raise AssertionError("z_slice outside the grid must be rejected")
+            except pkg().FluidSolverError:
+                pass

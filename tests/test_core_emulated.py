@@ -100,3 +100,8 @@ def test_abi_errors(emul_lib, pkg):
         with pytest.raises(pkg.FluidSolverError):
             s.op_set_bnd("density", 3)                          # b = 3 needs a z axis
         assert b"" != s.lib.fs_last_error(s.h)
+
+
+@pytest.mark.parametrize("dims", [(24, 20, 1), (16, 12, 9)])
+def test_visualize(emul_lib, oracle, dims):
+    P.case_visualize(emul_lib, oracle, *dims)

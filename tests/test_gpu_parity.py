@@ -187,3 +187,9 @@ def test_denormal_and_zero_fields_are_exact(lib, oracle):
         s.set_field("vx", x0)
         s.op_diffuse("vx0", "vx", 0, 1e-4, 0.1)
         P.assert_exact(s.get_field("vx0"), oracle.diffuse(0, x0, 1e-4, 0.1, mask, 20), "denormal diffuse")
+
+
+@pytest.mark.parametrize("dims", [(24, 20, 1), (192, 192, 1), (64, 40, 35)])
+def test_visualize(lib, oracle, dims):
+    """next row N2: UpdateVisualizationJob on the device."""
+    P.case_visualize(lib, oracle, *dims)
