@@ -27,6 +27,7 @@ EXPORTS = [
     "fs_abi_version", "fs_create", "fs_destroy", "fs_reset", "fs_last_error", "fs_slab_range",
     "fs_set_obstacles", "fs_add_density", "fs_add_velocity", "fs_add_source_cells", "fs_add_sources",
     "fs_step", "fs_sync", "fs_get_field", "fs_set_field", "fs_get_field_async", "fs_wait_transfers", "fs_get_metrics",
+    "fs_render_rgba",
     "fs_op_set_bnd", "fs_op_diffuse", "fs_op_smooth", "fs_op_lin_solve", "fs_op_project", "fs_op_advect",
     "fs_op_advect_velocity", "fs_op_enforce_obstacles",
     "fs_timer_start", "fs_timer_stop", "fs_launch_count", "fs_bench_sweep",
