@@ -214,6 +214,15 @@ class FluidSimulation:
         mean, mx, _ = self.native.metrics()
         return mean, mx
 
+    def UpdateVisualization(self, vis=None, z_slice=None):
+        """:755-853 -- the colour mapping job on the device; returns (ny, nx, 4) RGBA floats (Color[] layout)."""
+        vis = vis or native.FsVisParams.reference_defaults(self.currentSize)
+        vis.source_x, vis.source_y = self.sourcePositionX * self.currentSize, self.sourcePositionY * self.currentSize
+        vis.enable_custom_source = int(self.enableCustomSource)
+        if self.currentDepth > 1:
+            vis.z_slice = self.currentDepth // 2 if z_slice is None else z_slice
+        return self.native.render_rgba(vis)
+
     def close(self):
         if self.native is not None:
             self.native.close()
