@@ -380,6 +380,11 @@ struct CudaExec {
             reinterpret_cast<float4 *>(rgba)[t] = make_float4(c.r, c.g, c.b, c.a);
         });
     }
+    void streamlines(const FsGrid &g, int skip, float scale, const float *ux, const float *uy, const uint8_t *mask, float *out,
+                     long long count) {
+        const int nx = g.nx, ny = g.ny;
+        linear(count, [=] __device__(long long t) { fs_streamline_glyph(nx, ny, skip, scale, ux, uy, mask, (int)t, out + 4 * t); });
+    }
     void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
         const long long n = g.sz * g.nzl;
         linear(n, [=] __device__(long long t) {

@@ -94,6 +94,11 @@ int fs_wait_transfers(fs_solver *s) { FS_GUARD(s); c.ex.wait_transfers(); return
 
 int fs_render_rgba(fs_solver *s, const fs_vis_params *vp, float *out_rgba, int64_t n) { FS_GUARD(s); return c.render(vp, out_rgba, n); }
 
+int fs_streamlines(fs_solver *s, int32_t skip, float scale, int32_t z_slice, float *out_segments, int64_t count) {
+    FS_GUARD(s);
+    return c.streamlines(skip, scale, z_slice, out_segments, count);
+}
+
 int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density) {
     FS_GUARD(s);
     double sum = 0.0;

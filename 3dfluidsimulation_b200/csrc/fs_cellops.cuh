@@ -11,6 +11,7 @@
 // suite can compile them with g++ (tests/host_emul) and check the ring/obstacle logic against the
 // oracle without a GPU.  The product only ever runs them on the device.
 #pragma once
+#include <math.h>
 #include <stdint.h>
 
 #include "../../include/fluidsolver.h"
@@ -414,4 +415,30 @@ FS_HD FsColor fs_visualize_cell(const fs_vis_params &vp, float d, float p, bool 
         if (distSq < vp.visual_marker_radius * vp.visual_marker_radius) px = fs_color4(vp.source_position_color);
     }
     return px;
+}
+
+// ---- streamline glyphs (next row N3) ---------------------------------------------------------------------------
+// StreamlineCalculationJob.Execute (:1680-1727) followed by StreamlineDrawJob.Execute (:1739-1762) for glyph `index`
+// of one xy plane: out = (startX, startY, endX, endY), or (-1,-1,-1,-1) for a glyph the reference marks invalid
+// (outside the interior, obstacle cell, |V| < 0.01).  cols = nx / skip generalises the reference's size / skip.
+FS_HD void fs_streamline_glyph(int nx, int ny, int skip, float scale, const float *vx, const float *vy,
+                               const uint8_t *mask, int index, float out[4]) {
+    const int cols = nx / skip;
+    const int x = index % cols, y = index / cols;
+    const int i = x * skip + skip, j = y * skip + skip;
+    out[0] = out[1] = out[2] = out[3] = -1.0f;
+    if (i <= 0 || i >= nx - 1 || j <= 0 || j >= ny - 1) return;
+    const long long idx = i + (long long)j * nx;
+    if (mask[idx]) return;
+    const float ux = vx[idx], uy = vy[idx];
+    const float magnitude = sqrtf(ux * ux + uy * uy);
+    if (magnitude < 0.01f) return;
+    const float cap = (float)(skip - 1), want = magnitude * scale;
+    const float lineLength = cap < want ? cap : want; // math.min(skip - 1, magnitude * streamlineScale)
+    if (lineLength <= 0.0f) return;                   // StreamlineDrawJob: w <= 0 is invalid
+    const float angle = atan2f(uy, ux);
+    out[0] = (float)i;
+    out[1] = (float)j;
+    out[2] = (float)i + cosf(angle) * lineLength;
+    out[3] = (float)j + sinf(angle) * lineLength;
 }

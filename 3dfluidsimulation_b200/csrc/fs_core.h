@@ -334,6 +334,24 @@ struct SolverCore {
         return check();
     }
 
+    // ---- streamline glyphs (next row N3) -------------------------------------------------------------------
+    int streamlines(int skip, float scale, int z_slice, float *out, long long count) {
+        if (skip < 1 || !out) return fail(FS_ERR_BAD_ARGUMENT, "skip >= 1 and a destination are required");
+        const long long want = (long long)(g.nx / skip) * (g.ny / skip);
+        if (count != want) return fail(FS_ERR_BAD_ARGUMENT, "count must equal (nx/skip)*(ny/skip)");
+        int kl = 0;
+        if (g.hz) {
+            if (z_slice < zb || z_slice >= ze) return fail(FS_ERR_BAD_ARGUMENT, "z_slice is not owned by this handle");
+            kl = z_slice - g.zoff;
+        }
+        if (count == 0) return FS_OK;
+        float *dev = (float *)ex.render_buffer(sizeof(float) * 4 * (size_t)count);
+        if (!dev) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
+        ex.streamlines(g, skip, scale, vx + g.sz * kl, vy + g.sz * kl, mask + g.sz * kl, dev, count);
+        ex.download(out, dev, sizeof(float) * 4 * (size_t)count);
+        return check();
+    }
+
     // ---- field access -----------------------------------------------------------------------------
     float *field_ptr(int f) {
         switch (f) {

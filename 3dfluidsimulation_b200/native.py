@@ -27,7 +27,7 @@ EXPORTS = [
     "fs_abi_version", "fs_create", "fs_destroy", "fs_reset", "fs_last_error", "fs_slab_range",
     "fs_set_obstacles", "fs_add_density", "fs_add_velocity", "fs_add_source_cells", "fs_add_sources",
     "fs_step", "fs_sync", "fs_get_field", "fs_set_field", "fs_get_field_async", "fs_wait_transfers", "fs_get_metrics",
-    "fs_render_rgba",
+    "fs_render_rgba", "fs_streamlines",
     "fs_op_set_bnd", "fs_op_diffuse", "fs_op_smooth", "fs_op_lin_solve", "fs_op_project", "fs_op_advect",
     "fs_op_advect_velocity", "fs_op_enforce_obstacles",
     "fs_timer_start", "fs_timer_stop", "fs_launch_count", "fs_bench_sweep",
@@ -120,6 +120,7 @@ def load(path: str | None = None) -> C.CDLL:
         "fs_wait_transfers": (C.c_int, [vp]),
         "fs_get_metrics": (C.c_int, [vp, _F, _F, C.POINTER(C.c_double)]),
         "fs_render_rgba": (C.c_int, [vp, C.POINTER(FsVisParams), vp, i64]),
+        "fs_streamlines": (C.c_int, [vp, i32, f32, i32, vp, i64]),
         "fs_op_set_bnd": (C.c_int, [vp, i32, i32]),
         "fs_op_diffuse": (C.c_int, [vp, i32, i32, i32, f32, f32]),
         "fs_op_smooth": (C.c_int, [vp, i32, i32, i32, f32, f32, i32]),
@@ -256,6 +257,13 @@ class NativeSolver:
         if out is None:
             out = np.empty((self.ny, self.nx, 4), np.float32)
         self._ck(self.lib.fs_render_rgba(self.h, C.byref(vis), _ptr(out, np.float32), out.size))
+        return out
+
+    def streamlines(self, skip, scale, z_slice=0) -> np.ndarray:
+        """Streamline glyph segments of one plane: (count, 4) float32 rows (startX, startY, endX, endY), -1 = invalid."""
+        count = (self.nx // skip) * (self.ny // skip)
+        out = np.empty((count, 4), np.float32)
+        self._ck(self.lib.fs_streamlines(self.h, skip, scale, z_slice, _ptr(out, np.float32), count))
         return out
 
     def metrics(self):

@@ -214,6 +214,38 @@ class FluidSimulation:
         mean, mx, _ = self.native.metrics()
         return mean, mx
 
+    def DrawStreamlines(self, streamlineDensity=4, streamlineScale=1.0, streamlineThickness=1.0, z_slice=None):
+        """:886-959 -- glyph segments from the device (fs_streamlines), then the reference's host-side Bresenham
+        drawing (:1765-1849).  Returns a (size, size) uint8 coverage mask (1 where streamlineColor is painted)."""
+        n = self.currentSize
+        skip = max(1, n // (streamlineDensity * 10))                                   # :892
+        k = 0 if self.currentDepth == 1 else (self.currentDepth // 2 if z_slice is None else z_slice)
+        seg = self.native.streamlines(skip, streamlineScale, k)
+        tex = np.zeros((n, n), np.uint8)
+        half = int(math.floor(streamlineThickness / 2))
+        for sx, sy, ex, ey in seg:
+            if sx < 0:
+                continue
+            x0, y0, x1, y1 = int(sx), int(sy), int(np.rint(ex)), int(np.rint(ey))      # math.round: half to even
+            steep = abs(y1 - y0) > abs(x1 - x0)
+            if steep:
+                x0, y0, x1, y1 = y0, x0, y1, x1
+            if x0 > x1:
+                x0, x1, y0, y1 = x1, x0, y1, y0
+            dx, dy = x1 - x0, abs(y1 - y0)
+            err, y, ystep = dx // 2, y0, (1 if y0 < y1 else -1)
+            for x in range(x0, x1 + 1):
+                for tx in range(-half, half + 1):
+                    for ty in range(-half, half + 1):
+                        px, py = (y + tx, x + ty) if steep else (x + tx, y + ty)
+                        if 0 <= px < n and 0 <= py < n:
+                            tex[py, px] = 1
+                err -= dy
+                if err < 0:
+                    y += ystep
+                    err += dx
+        return tex
+
     def UpdateVisualization(self, vis=None, z_slice=None):
         """:755-853 -- the colour mapping job on the device; returns (ny, nx, 4) RGBA floats (Color[] layout)."""
         vis = vis or native.FsVisParams.reference_defaults(self.currentSize)

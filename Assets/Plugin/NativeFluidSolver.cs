@@ -76,6 +76,8 @@ namespace FluidSolverNative
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_wait_transfers(SolverHandle s);
         // device-side UpdateVisualizationJob: one xy plane as RGBA floats (Color[] layout); vp = fs_vis_params blob (see include/fluidsolver.h)
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_render_rgba(SolverHandle s, IntPtr visParams, [Out] Color[] outRgba, long n);
+        // device-side StreamlineCalculationJob + StreamlineDrawJob: count*4 floats (x0, y0, x1, y1), -1 = invalid glyph
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_streamlines(SolverHandle s, int skip, float scale, int zSlice, [Out] float[] segments, long count);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_metrics(SolverHandle s, out float meanDensity, out float maxSpeed, out double sumDensity);
 
         // operator entry points (one reference job chain each); used by tests and by hosts that compose their own step

@@ -143,6 +143,13 @@ typedef struct fs_vis_params {
 /* out_rgba: nx*ny*4 floats, n = nx*ny*4. */
 int fs_render_rgba(fs_solver *s, const fs_vis_params *vp, float *out_rgba, int64_t n);
 
+/* ---- streamline glyphs: StreamlineCalculationJob + StreamlineDrawJob,
+ * FluidSim.cs:1668-1763, on the device for plane z_slice (ignored when nz == 1).  skip = max(1, size/(streamlineDensity*10))
+ * and scale = streamlineScale as in DrawStreamlines (:892, :925).  out_segments: count*4 floats
+ * (startX, startY, endX, endY), (-1,-1,-1,-1) for glyphs the reference marks invalid; count must equal
+ * (nx/skip)*(ny/skip).  The Bresenham drawing of the segments (:1765-1849) stays on the host, as in the reference. */
+int fs_streamlines(fs_solver *s, int32_t skip, float scale, int32_t z_slice, float *out_segments, int64_t count);
+
 /* ---- metrics: LogCurrentMetrics, FluidSim.cs:582-594 (mean density, max |V|) over owned voxels;
  * sum_density is returned so that slabs can be combined. */
 int fs_get_metrics(fs_solver *s, float *mean_density, float *max_speed, double *sum_density);

@@ -162,6 +162,13 @@ def visualize(density, pressure, obstacles, vis):
     return out
 
 
+def streamlines(vx, vy, obstacles, skip, scale):
+    ny, nx = vx.shape
+    out = np.empty(((nx // skip) * (ny // skip), 4), np.float32)
+    lib().fo_streamlines(nx, ny, int(skip), _cf(scale), _f(vx), _f(vy), _u(obstacles), out.ctypes.data_as(_F))
+    return out
+
+
 def cell_index(shape, x, y, z=0.0):
     nx, ny, nz = _dims(shape)
     return int(lib().fo_cell_index(nx, ny, nz, _cf(x), _cf(y), _cf(z)))

@@ -487,3 +487,30 @@ void fo_visualize(int nx, int ny, const float *density, const float *pressure, c
         out[4 * index] = px.r; out[4 * index + 1] = px.g; out[4 * index + 2] = px.b; out[4 * index + 3] = px.a;
     }
 }
+
+/* ---- streamline glyphs: StreamlineCalculationJob + StreamlineDrawJob, FluidSim.cs:1680-1762 (next row N3) -------
+ * out: count*4 floats (startX, startY, endX, endY), -1 x4 for invalid glyphs; count = (nx/skip)*(ny/skip). */
+void fo_streamlines(int nx, int ny, int skip, float streamlineScale, const float *velocX, const float *velocY,
+                    const uint8_t *obstacles, float *out) {
+    const int cols = nx / skip, rows = ny / skip;
+    for (int index = 0; index < cols * rows; index++) {
+        float sx = 0, sy = 0, sz = 0, sw = 0; /* the float4 `streamline` of :1726 */
+        const int x = index % cols, y = index / cols;
+        const int i = x * skip + skip, j = y * skip + skip;
+        sx = (float)i; sy = (float)j;
+        if (!(i <= 0 || i >= nx - 1 || j <= 0 || j >= ny - 1) && !obstacles[i + j * nx]) {
+            const float vx = velocX[i + j * nx], vy = velocY[i + j * nx];
+            const float magnitude = sqrtf(vx * vx + vy * vy);
+            if (!(magnitude < 0.01f)) {
+                sw = fminf((float)(skip - 1), magnitude * streamlineScale);
+                sz = atan2f(vy, vx);
+            }
+        }
+        float *o = out + 4 * index;
+        if (sw <= 0) { o[0] = o[1] = o[2] = o[3] = -1.0f; continue; } /* :1744-1749 */
+        const int startX = (int)sx, startY = (int)sy;
+        o[0] = (float)startX; o[1] = (float)startY;
+        o[2] = startX + cosf(sz) * sw;
+        o[3] = startY + sinf(sz) * sw;
+    }
+}

@@ -34,6 +34,9 @@ typedef struct fo_vis_params {
 void fo_visualize(int nx, int ny, const float *density, const float *pressure, const uint8_t *obstacles,
                   const fo_vis_params *vp, float *out);
 
+void fo_streamlines(int nx, int ny, int skip, float streamlineScale, const float *velocX, const float *velocY,
+                    const uint8_t *obstacles, float *out);
+
 void fo_set_bnd(int nx, int ny, int nz, int b, float *x, const uint8_t *obs);
 void fo_diffuse_coeffs(int n, float diff, float dt, float *a, float *c);
 void fo_diffuse_smooth(int nx, int ny, int nz, int b, float *x, const float *x0, float a, float c,

@@ -108,6 +108,10 @@ struct HostExec {
             rgba[4 * t] = c.r; rgba[4 * t + 1] = c.g; rgba[4 * t + 2] = c.b; rgba[4 * t + 3] = c.a;
         }
     }
+    void streamlines(const FsGrid &g, int skip, float scale, const float *ux, const float *uy, const uint8_t *mask, float *out,
+                     long long count) {
+        for (long long t = 0; t < count; t++) fs_streamline_glyph(g.nx, g.ny, skip, scale, ux, uy, mask, (int)t, out + 4 * t);
+    }
     void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
         for (int kl = 0; kl < g.nzl; kl++)
             for (int j = 0; j < g.ny; j++)

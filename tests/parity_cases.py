@@ -358,3 +358,25 @@ def case_visualize(lib, O, nx=24, ny=20, nz=1):
                 raise AssertionError("z_slice outside the grid must be rejected")
             except pkg().FluidSolverError:
                 pass
+
+
+def case_streamlines(lib, O, nx=40, ny=32, nz=1):
+    """fs_streamlines (StreamlineCalculationJob + StreamlineDrawJob on the device) vs the oracle.  The glyph validity
+    pattern and start points are exact; end points involve atan2/cos/sin and agree to 1e-4 pixels."""
+    rng = np.random.default_rng(41)
+    shape = shape_of(nx, ny, nz)
+    with make_solver(lib, nx, ny, nz) as s:
+        ux, uy = rnd(shape, rng, 3.0), rnd(shape, rng, 3.0)
+        ux[np.abs(ux) < 0.3] = 0; uy[np.abs(uy) < 0.3] = 0      # some glyphs fall under the 0.01 magnitude cut
+        m = (rng.random(shape) < 0.15).astype(np.uint8)
+        s.set_obstacles(m); s.set_field("vx", ux); s.set_field("vy", uy)
+        k = nz // 2 if nz > 1 else 0
+        pl = (lambda a: a[k]) if nz > 1 else (lambda a: a)
+        for skip, scale in ((1, 1.0), (3, 1.0), (4, 2.5), (7, 10.0)):
+            got = s.streamlines(skip, scale, k)
+            want = O.streamlines(pl(ux), pl(uy), pl(m), skip, scale)
+            assert got.shape == want.shape
+            assert_exact(got[:, :2], want[:, :2], f"streamline starts skip={skip}")
+            assert np.array_equal(got[:, 2] < 0, want[:, 2] < 0), f"streamline validity pattern skip={skip}"
+            err = float(np.abs(got[:, 2:] - want[:, 2:]).max()) if got.size else 0.0
+            assert err <= 1e-4, f"streamline ends skip={skip}: {err}"

@@ -105,3 +105,8 @@ def test_abi_errors(emul_lib, pkg):
 @pytest.mark.parametrize("dims", [(24, 20, 1), (16, 12, 9)])
 def test_visualize(emul_lib, oracle, dims):
     P.case_visualize(emul_lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", [(40, 32, 1), (24, 20, 9)])
+def test_streamlines(emul_lib, oracle, dims):
+    P.case_streamlines(emul_lib, oracle, *dims)

@@ -193,3 +193,9 @@ def test_denormal_and_zero_fields_are_exact(lib, oracle):
 def test_visualize(lib, oracle, dims):
     """next row N2: UpdateVisualizationJob on the device."""
     P.case_visualize(lib, oracle, *dims)
+
+
+@pytest.mark.parametrize("dims", [(40, 32, 1), (192, 192, 1), (64, 40, 35)])
+def test_streamlines(lib, oracle, dims):
+    """next row N3: streamline glyph segments on the device."""
+    P.case_streamlines(lib, oracle, *dims)
