@@ -199,3 +199,27 @@ def test_visualize(lib, oracle, dims):
 def test_streamlines(lib, oracle, dims):
     """next row N3: streamline glyph segments on the device."""
     P.case_streamlines(lib, oracle, *dims)
+
+
+def test_cpp_host_on_gpu(lib, tmp_path):
+    """The compiled-language host mirror (include/fluid_simulation.hpp) linked against the product library gives
+    the same fields as the Python mirror on the same GPU."""
+    import subprocess
+
+    from conftest import ROOT
+
+    exe = str(tmp_path / "host_demo_cuda")
+    subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "host_demo.cpp"), "-o", exe, "-L", os.path.dirname(lib), "-lfluidsolver",
+                    f"-Wl,-rpath,{os.path.dirname(lib)}", "-Wl,-rpath-link,/usr/local/cuda/lib64"], check=True)
+    out = subprocess.run([exe, "64", "3", "1"], capture_output=True, text=True, check=True).stdout
+    got = {l.split()[0]: [float(v) for v in l.split()[1:]] for l in out.strip().splitlines()}
+    sim = P.pkg().FluidSimulation(size=64, lib_path=lib, use_cuda_graph=False)
+    sim.enableCustomSource = True; sim.sourceEmitsVelocity = True
+    sim.sourceDirection = 90.0; sim.sourceRadius = 2.0; sim.sourcePositionY = 0.2
+    for _ in range(3):
+        sim.Update()
+    for name in ("density", "vx", "vy", "pressure"):
+        a = sim.field(name).astype(np.float64)
+        np.testing.assert_allclose(got[name], [a.sum(), (a * a).sum()], rtol=2e-5, atol=1e-12, err_msg=name)
+    sim.close()
