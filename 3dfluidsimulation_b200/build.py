@@ -48,12 +48,18 @@ def is_stale() -> bool:
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", LIB, os.path.join(CSRC, "fluidsolver.cu")]
+    # build into a private file and rename it into place: a concurrent process (another torchrun rank, a test
+    # worker) either sees the old complete library or the new complete one, never a half-written file
+    tmp = f"{LIB}.{os.getpid()}.tmp"
+    cmd = [nvcc_path(), *NVCC_FLAGS, "-ccbin", "/usr/bin/g++", "-o", tmp, os.path.join(CSRC, "fluidsolver.cu")]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         print(r.stdout + r.stderr)
     return LIB

@@ -172,7 +172,11 @@ struct CudaExec {
         if (halo_on && my_flags) {
             unsigned e = 0;
             FS_CUDA(cudaMemcpy(&e, my_flags + FS_HF_ERROR, sizeof(e), cudaMemcpyDeviceToHost));
-            if (e && !bad) { bad = true; msg = "advection back-trace left the neighbouring slab (slab too thin for this CFL)"; }
+            if (e && !bad) {
+                bad = true;
+                msg = e == 2 ? "halo exchange timed out: a neighbouring slab did not publish its planes (rank missing or failed)"
+                             : "advection back-trace left the neighbouring slab (slab too thin for this CFL)";
+            }
         }
     }
     void *get_scratch(size_t bytes) {

@@ -92,6 +92,8 @@ struct SolverCore {
         ex.free(obst_list);
         obst_list = nullptr; n_obst = 0; any_obstacle = false;
         g_any_obstacle = g_interior_obstacle = false;
+        // captured graphs hold the freed obstacle list and the mirror / enforce / halo decisions taken with it
+        ex.invalidate_graph();
         return check();
     }
 
@@ -233,7 +235,12 @@ struct SolverCore {
         tmp = wr;
     }
     void lin_solve_rb(int b, float *x, const float *rhs, float a, float c, int iters, bool zero_guess) {
-        if (zero_guess) ex.zero(x, sizeof(float) * nloc);
+        if (zero_guess) {
+            ex.zero(x, sizeof(float) * nloc);
+            // slabs: a faster neighbour must not store its first boundary plane into this slab's ghost plane before
+            // the memset above has run (it would be wiped): nobody passes the fence before everybody has zeroed
+            ex.halo_fence();
+        }
         for (int it = 0; it < iters; it++) {
             bool ringed = false;
             for (int colour = 0; colour < 2; colour++) {

@@ -114,10 +114,22 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 //     seq = flags[FS_HF_BASE] + op_offset
 // (FS_HF_BASE lives in device memory and is advanced by halo_commit_kernel, so a CUDA graph replays with
 // fresh numbers).  Protocol of operation `seq` on every rank ("strict lock step"):
-//   wait   flags[FROM_LO] >= seq-1 and flags[FROM_HI] >= seq-1   (neighbours finished op seq-1: their
-//          stores into my ghosts have landed AND they no longer read the ghosts I am about to overwrite)
-//   store  my lowest owned plane -> lower neighbour's top ghost plane, my highest -> upper's plane 0
+//   wait   flags[FROM_LO] >= seq-1 and flags[FROM_HI] >= seq-1   (the neighbours' stores of op seq-1 have landed here;
+//          redundant after a push of op seq-1, which already blocked on the same words -- it only matters for the
+//          first op after fs_halo_connect)
+//   store  my lowest owned planes -> lower neighbour's top ghost planes, my highest -> upper's bottom ghost planes
 //   signal __threadfence_system(); neighbour.flags[FROM_HI or FROM_LO] = seq
+//   wait   flags[FROM_*] >= seq   (the neighbours' planes of THIS op have landed: the kernel does not retire earlier)
+// What the signal does NOT say: that the neighbour has finished READING the ghost planes a later push overwrites.
+// Write-after-read safety of the ghosts comes from the solver's buffer discipline instead, and every new halo
+// producing op has to respect it:
+//   * ping-pong sweeps (smoother / Jacobi / fused pair): op seq+1 writes the ghosts of the OTHER buffer; the ghosts of
+//     a buffer are rewritten two ops later, and the neighbour cannot have signalled op seq+1 before the kernels of
+//     op seq that read them were complete (its push of seq+1 is stream-ordered after them);
+//   * in-place kernels (red-black colour passes, mirror, gradient, obstacle pass) re-push planes whose ghost copies
+//     are only read by kernels ordered BEFORE the neighbour's previous signal, or carry identical values.
+// An in-place op followed by a halo of a field whose ghost a neighbour kernel may still be reading would race; such
+// an op needs a halo_fence() (consumer-done) first.
 // For the relaxation sweeps a slab forks: side stream = boundary-chunk launch of relax_vec4 -> halo_push_kernel
 // (wait seq-1, store, signal seq, wait for the incoming seq); main stream = interior-chunk launch; join.  The two
 // launches run concurrently, so the exchange is hidden behind the interior chunks.  (Fusing the three steps INTO relax_vec4 was built and measured: any
@@ -142,8 +154,27 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ void halo_spin_until(const unsigned *flag, unsigned target) {
-    while ((int)(ld_acquire_sys(flag) - target) < 0) __nanosleep(64);
+__device__ __forceinline__ unsigned long long fs_globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Bounded: a neighbour that died or never launched must not leave this GPU spinning for ever.  After
+// FS_HALO_TIMEOUT_NS the waiter records FS_HF_ERROR = 2 in its own flag block and carries on (the fields are then
+// wrong; fs_sync / fs_get_* report the error).
+#ifndef FS_HALO_TIMEOUT_NS
+#define FS_HALO_TIMEOUT_NS 30000000000ull
+#endif
+__device__ __forceinline__ void halo_spin_until(const unsigned *flag, unsigned target, unsigned *err_word) {
+    if ((int)(ld_acquire_sys(flag) - target) >= 0) return;
+    const unsigned long long t0 = fs_globaltimer_ns();
+    while ((int)(ld_acquire_sys(flag) - target) < 0) {
+        __nanosleep(64);
+        if (fs_globaltimer_ns() - t0 > FS_HALO_TIMEOUT_NS) {
+            *(volatile unsigned *)err_word = 2u;
+            return;
+        }
+    }
 }
 __device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
     return *(volatile const unsigned *)(h.my_flags + FS_HF_BASE) + h.op_offset;
@@ -156,8 +187,8 @@ halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const flo
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) {
         const unsigned seq = halo_seq(h);
-        if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1);
-        if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1);
+        if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
+        if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
         s_seq = seq;
     }
     __syncthreads();
@@ -180,8 +211,8 @@ halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const flo
             if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
             // ... and do not retire before the neighbours' planes of the same op have landed here: whatever
             // is ordered after this kernel may read the ghost planes (no separate wait launch needed)
-            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq);
-            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq);
+            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
+            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
         }
     }
 }
@@ -240,7 +271,6 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     // extra ring rows this thread owns in y (set_bnd faces/edges), -1 = none
     const int jr = j == 1 ? 0 : (j == g.ny - 2 ? g.ny - 1 : -1);
     const int jr2 = (j == 1 && j == g.ny - 2) ? g.ny - 1 : -1; // ny == 3: both
-    const bool xy_plain = !first_x && !last_x && jr < 0;
 
     const long long idx0 = fs_idx(g, x0, j, k_lo);
     // per-thread running pointers (one 64-bit add each per plane instead of re-deriving every address)
@@ -300,7 +330,11 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 
         const int k = kl + g.zoff;
         const int kr = HZ ? (k == 1 ? kl - 1 : (k == g.nz - 2 ? kl + 1 : -1)) : -1;
-        if (xy_plain && kr < 0) { // interior thread, interior plane: one plain store
+        if (jr < 0 && kr < 0) { // no y/z ring row derives from this row: one store.  The x-face cells (x = 0, nx-1) are
+            // lanes of the same float4 and are fixed up in place (fs_ring_value with fx only); sending every x-edge
+            // WARP through the generic ring path below cost half the warps of a 512-wide grid ~100 issue slots per plane
+            if (first_x) v[0] = b == 1 ? -v[1] : v[1];
+            if (last_x) v[3] = b == 1 ? -v[2] : v[2];
             st4(pout, v);
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
@@ -347,7 +381,9 @@ __device__ __forceinline__ FsVec4Pos fs_vec4_pos(const FsGrid &g, int x0, int j,
 }
 // Stores the row and every set_bnd ring row / lane that derives from it (ring scatter, b = field kind).
 __device__ __forceinline__ void fs_vec4_store_ring(float *out, const FsGrid &g, const FsVec4Pos &p, float v[4], int b) {
-    if (!p.first_x && !p.last_x && p.jr < 0 && p.kr < 0) {
+    if (p.jr < 0 && p.kr < 0) { // x-face lanes are fixed up in place, see relax_vec4
+        if (p.first_x) v[0] = b == 1 ? -v[1] : v[1];
+        if (p.last_x) v[3] = b == 1 ? -v[2] : v[2];
         st4(out + fs_idx(g, p.x0, p.j, p.kl), v);
         return;
     }

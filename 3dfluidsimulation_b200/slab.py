@@ -38,7 +38,15 @@ class SlabGroup:
 
     def __init__(self, nx, ny, nz, count, *, devices=None, lib_path=None, **kw):
         self.count, self.nx, self.ny, self.nz = count, nx, ny, nz
-        devices = devices or [0] * count
+        lib = native.load(lib_path)
+        emulated = hasattr(lib, "fs_host_emulation")   # tests/host_emul: host threads, no devices involved
+        devices = list(devices) if devices is not None else ([0] * count if emulated else list(range(count)))
+        if len(devices) != count:
+            raise ValueError("one device per slab is required")
+        if not emulated and len(set(devices)) != count:
+            # every slab's halo kernel spins on flags its neighbours' kernels write; kernels of different handles on
+            # ONE GPU are not guaranteed to be co-resident, so two slabs sharing a device can deadlock
+            raise ValueError("z-slabs need distinct devices (slabs that wait on one another cannot share a GPU)")
         self.solvers = [native.NativeSolver(nx, ny, nz, slab_rank=r, slab_count=count, device_id=devices[r],
                                             lib_path=lib_path, **kw) for r in range(count)]
         self.pool = ThreadPoolExecutor(max_workers=count)

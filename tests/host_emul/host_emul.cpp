@@ -231,3 +231,7 @@ struct HostExec {
 
 #define FS_EXEC HostExec
 #include "../../3dfluidsimulation_b200/csrc/fs_abi.inl"
+
+// marks this library as the CPU test scaffold (3dfluidsimulation_b200/slab.py uses it to allow several slab
+// handles without distinct CUDA devices)
+extern "C" int fs_host_emulation(void) { return 1; }

@@ -183,8 +183,22 @@ def case_sources(lib, O, nx, ny, nz):
         assert_exact(s.get_field("density"), o.f["density"], "dense add")
 
 
+def plume_cells(nx, ny, nz):
+    """Smoke-plume source cells: ball at (0.5 nx, 0.2 ny, 0.5 nz), r = max(1.5, nx/16), linear
+    fall-off 1 - dist/r as in UpdateCustomSource (FluidSim.cs:503-512).  Integer cell coordinates as float32."""
+    sx, sy, sz, rad = 0.5 * nx, 0.2 * ny, 0.5 * nz, max(1.5, nx / 16)
+    r = int(np.ceil(rad)) + 1
+    ks = np.arange(max(int(sz) - r, 0), min(int(sz) + r, nz - 1) + 1) if nz > 1 else np.array([0])
+    js = np.arange(max(int(sy) - r, 0), min(int(sy) + r, ny - 1) + 1)
+    is_ = np.arange(max(int(sx) - r, 0), min(int(sx) + r, nx - 1) + 1)
+    kk, jj, ii = np.meshgrid(ks, js, is_, indexing="ij")
+    d = np.sqrt((ii - sx) ** 2 + (jj - sy) ** 2 + ((kk - sz) ** 2 if nz > 1 else 0.0))
+    keep = d <= rad
+    return (ii[keep].astype(f32), jj[keep].astype(f32), kk[keep].astype(f32), (1.0 - d[keep] / rad).astype(f32))
+
+
 def run_steps(lib, O, nx, ny, nz, steps, *, kd=20, kp=20, obstacles=True, use_graph=False, seed=6, dt=0.1,
-              visc=1e-4, diff=1e-4, solver_kwargs=None):
+              visc=1e-4, diff=1e-4, vsrc=1.0, solver_kwargs=None, oracle_kwargs=None):
     """Plume in Update() order (sources, then the step) on solver and oracle; returns both."""
     rng = np.random.default_rng(seed)
     shape = shape_of(nx, ny, nz)
@@ -194,29 +208,23 @@ def run_steps(lib, O, nx, ny, nz, steps, *, kd=20, kp=20, obstacles=True, use_gr
             yy, xx = np.meshgrid(np.arange(ny), np.arange(nx), indexing="ij")
             mask = (((xx - 0.5 * nx) ** 2 + (yy - 0.5 * ny) ** 2) < (0.1 * nx) ** 2).astype(np.uint8)
         else:
-            zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+            zz, yy, xx = np.ogrid[:nz, :ny, :nx]   # broadcast: no nx*ny*nz index arrays (512^3 would need 3 GB)
             mask = (((xx - 0.5 * nx) ** 2 + (yy - 0.5 * ny) ** 2 + (zz - 0.5 * nz) ** 2) < (0.1 * nx) ** 2).astype(np.uint8)
     s = make_solver(lib, nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=obstacles,
                     cell_size=1.0 / nx, use_cuda_graph=use_graph, **(solver_kwargs or {}))
-    o = O.OracleSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=obstacles, cell_size=1.0 / nx)
+    o = O.OracleSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=obstacles, cell_size=1.0 / nx,
+                       **(oracle_kwargs or {}))
     s.set_obstacles(mask); o.obstacles[...] = mask
     for name in ("vx", "vy") + (("vz",) if nz > 1 else ()):
         a = rnd(shape, rng, 0.01)
         s.set_field(name, a); o.f[name][...] = a
-    sx, sy, sz, rad = 0.5 * nx, 0.2 * ny, 0.5 * nz, max(1.5, nx / 16)
-    cells = []
-    for k in range(nz):
-        for j in range(ny):
-            for i in range(nx):
-                d = np.sqrt((i - sx) ** 2 + (j - sy) ** 2 + ((k - sz) ** 2 if nz > 1 else 0.0))
-                if d <= rad:
-                    cells.append((i, j, k, 1.0 - d / rad))
-    cx = np.array([c[0] for c in cells], f32); cy = np.array([c[1] for c in cells], f32); cz = np.array([c[2] for c in cells], f32)
-    fall = np.array([c[3] for c in cells], f32)
+    cx, cy, cz, fall = plume_cells(nx, ny, nz)
+    dens, vyamt = (f32(100) * fall).astype(f32), (f32(vsrc) * fall).astype(f32)
+    flat = (cz.astype(np.int64) * ny + cy.astype(np.int64)) * nx + cx.astype(np.int64)   # unique cells: a fancy += is exact
     for _ in range(steps):
-        s.add_source_cells(cx, cy, cz, density=f32(100) * fall, ay=f32(1.0) * fall)
-        for x, y, z, f in zip(cx, cy, cz, fall):
-            o.add_density(x, y, z, f32(100) * f); o.add_velocity(x, y, z, 0.0, f32(1.0) * f, 0.0)
+        s.add_source_cells(cx, cy, cz, density=dens, ay=vyamt)
+        o.f["density"].reshape(-1)[flat] += dens
+        o.f["vy"].reshape(-1)[flat] += vyamt
         s.step(dt, visc, diff); o.step(dt, visc, diff)
     return s, o
 

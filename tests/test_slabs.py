@@ -23,7 +23,7 @@ def slab_mod():
 
 
 def run_group_vs_oracle(lib, O, nx, ny, nz, count, obstacles, vscale, steps=2, kd=4, kp=6, devices=None, graph=False,
-                        local_obstacle=False):
+                        local_obstacle=False, red_black=False):
     rng = np.random.default_rng(3)
     shape = (nz, ny, nx)
     mask = P.random_mask(shape, rng, 0.06) if obstacles else np.zeros(shape, np.uint8)
@@ -31,8 +31,10 @@ def run_group_vs_oracle(lib, O, nx, ny, nz, count, obstacles, vscale, steps=2, k
         mask = np.zeros(shape, np.uint8)
         mask[nz // 2 - 1:nz // 2 + 1, 3:6, 4:8] = 1
     g = slab_mod().SlabGroup(nx, ny, nz, count, lib_path=lib, devices=devices, iters_diffuse=kd, iters_pressure=kp,
-                             enable_obstacle=obstacles, cell_size=1.0 / nx, use_cuda_graph=graph)
-    o = O.OracleSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=obstacles, cell_size=1.0 / nx)
+                             enable_obstacle=obstacles, cell_size=1.0 / nx, use_cuda_graph=graph,
+                             solver_kind=1 if red_black else 0)
+    o = O.OracleSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=obstacles, cell_size=1.0 / nx,
+                       red_black=red_black)
     try:
         g.set_obstacles(mask); o.obstacles[...] = mask
         for n in ("density", "vx", "vy", "vz"):
@@ -56,6 +58,14 @@ def run_group_vs_oracle(lib, O, nx, ny, nz, count, obstacles, vscale, steps=2, k
 @pytest.mark.parametrize("obstacles", [False, True])
 def test_emulated_slabs_match_single_grid(emul_lib, oracle, count, obstacles):
     run_group_vs_oracle(emul_lib, oracle, 12, 10, 16, count, obstacles, vscale=1.5)
+
+
+@pytest.mark.parametrize("count", [2, 3])
+@pytest.mark.parametrize("kp", [5, 6])
+def test_emulated_slabs_red_black(emul_lib, oracle, count, kp):
+    """Red-black pressure solve (BASELINE config 5) across slabs: colour parity uses the GLOBAL z, halos travel
+    between the colour passes; the slab run equals the single-grid oracle."""
+    run_group_vs_oracle(emul_lib, oracle, 12, 10, 16, count, True, vscale=1.5, kp=kp, red_black=True)
 
 
 @pytest.mark.timeout(120)
@@ -147,6 +157,18 @@ def test_two_gpu_slabs_in_process(cuda_lib, oracle, obstacles, graph):
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     run_group_vs_oracle(cuda_lib, oracle, 64, 40, 48, 2, obstacles, vscale=3.0, steps=3, kd=6, kp=8, devices=[0, 1], graph=graph)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims,kp", [((64, 40, 48), 8), ((128, 128, 128), 100)])
+def test_two_gpu_slabs_red_black(cuda_lib, oracle, dims, kp):
+    """BASELINE config 5's solver over 2 slabs on 2 GPUs (P2P halos between the colour passes / fused sweeps):
+    equal to the single-grid oracle, 128^3 with K_p = 100 included."""
+    if _gpu_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    oracle.set_threads(os.cpu_count())
+    run_group_vs_oracle(cuda_lib, oracle, *dims, 2, True, vscale=1.0, steps=1, kd=4, kp=kp, devices=[0, 1], graph=True,
+                        red_black=True)
 
 
 IPC_WORKER = r'''
