@@ -37,6 +37,8 @@ struct CudaExec {
     int64_t launches = 0;
     bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
     int tune_zchunk = 0, tune_by = 0; // FS_ZCHUNK / FS_BLOCK_Y: override the sweep's z chunk length / CTA rows (experiments)
+    int pair_rows = FS_PAIR_MAX_ROWS, pair_zchunk = 0; // FS_PAIR_ROWS / FS_PAIR_ZCHUNK (experiments)
+    bool no_pair = false;       // FS_NO_PAIR=1: never use the fused two-stage sweep (tests compare both paths)
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
     bool use_graph = false;
@@ -98,6 +100,11 @@ struct CudaExec {
         force_generic = fg && fg[0] == '1';
         if (const char *e = getenv("FS_ZCHUNK")) tune_zchunk = atoi(e);
         if (const char *e = getenv("FS_BLOCK_Y")) tune_by = atoi(e);
+        if (const char *e = getenv("FS_PAIR_ROWS")) pair_rows = atoi(e);
+        if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
+        if (const char *e = getenv("FS_NO_PAIR")) no_pair = e[0] == '1';
+        if (pair_rows < 3) pair_rows = 3;
+        if (pair_rows > FS_PAIR_MAX_ROWS) pair_rows = FS_PAIR_MAX_ROWS;
         const char *la = getenv("FS_L2_AHEAD");
         if (la) l2_ahead = atoi(la);
         return bad ? 1 : 0;
@@ -272,6 +279,56 @@ struct CudaExec {
         else
             cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         if (fuse_halo) halo(g, out); // per-cell fallback: push after the whole sweep
+    }
+    // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
+    // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
+    bool pair_supported(const FsGrid &g, float c) const {
+        const bool c_ok = c != 0.0f && c == c && c - c == 0.0f;
+        return g.hz && g.nx % 4 == 0 && !force_generic && !no_pair && c_ok;
+    }
+    bool relax_pair(int kind, const FsGrid &g, const float *in, const float *rhs, float *out, const uint8_t *flags,
+                    float a, float c, int b, bool in_zero, bool fuse_halo) {
+        if (!pair_supported(g, c)) return false;
+        int kl0, cnt;
+        interior_planes(g, &kl0, &cnt);
+        if (cnt <= 0) return true;
+        const int ncols = g.nx / 4;
+        const int wcols = ncols < FS_PAIR_W ? ncols : FS_PAIR_W, cols = wcols + 2;
+        int rows = pair_rows;
+        if (rows > g.ny) rows = g.ny;                    // ny - 2 inner rows + the two ring rows
+        const int threads = ((cols * rows + 31) / 32) * 32;
+        const int gxn = (ncols + wcols - 1) / wcols, gyn = (g.ny - 2 + rows - 3) / (rows - 2);
+        // z chunk per CTA: stage 1 is evaluated on zchunk + 2 planes, so long chunks; but enough CTAs for ~2 waves
+        long long zchunk = (long long)cnt * gxn * gyn / ((long long)sm_count * 2);
+        if (zchunk < 8) zchunk = 8;
+        if (zchunk > 64) zchunk = 64;
+        if (halo_on && zchunk > cnt / 4) zchunk = cnt / 4 < 4 ? 4 : cnt / 4; // slabs: keep interior chunks to overlap the push
+        if (pair_zchunk > 0) zchunk = pair_zchunk;
+        if (zchunk > cnt) zchunk = cnt;
+        const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
+        const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
+#define FS_LAUNCH_PAIR(NZ_, BASE_, STRIDE_) \
+    do { const dim3 grid(gxn, gyn, NZ_); \
+         if (kind == FS_PAIR_JACOBI) relax_pair_kernel<FS_PAIR_JACOBI><<<grid, threads, 0, st>>>(g, in, rhs, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead, wcols, rows); \
+         else if (kind == FS_PAIR_SMOOTH) relax_pair_kernel<FS_PAIR_SMOOTH><<<grid, threads, 0, st>>>(g, in, nullptr, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead, wcols, rows); \
+         else relax_pair_kernel<FS_PAIR_RED_BLACK><<<grid, threads, 0, st>>>(g, in, rhs, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead, wcols, rows); \
+         launches++; } while (0)
+        if (halo_on && fuse_halo && nchunks > 2) {
+            FS_CUDA(cudaEventRecord(ev_fork, st));
+            FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
+            { cudaStream_t main_st = st; st = st_halo;
+              FS_LAUNCH_PAIR(2, 0, nchunks - 1);           // the two chunks holding the slab's boundary planes
+              st = main_st; }
+            halo_on_stream(g, out, st_halo);
+            FS_CUDA(cudaEventRecord(ev_join, st_halo));
+            FS_LAUNCH_PAIR(nchunks - 2, 1, 1);             // interior chunks, concurrently
+            FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+        } else {
+            FS_LAUNCH_PAIR(nchunks, 0, 1);
+            if (halo_on && fuse_halo) halo(g, out);
+        }
+#undef FS_LAUNCH_PAIR
+        return true;
     }
     // returns true when the launch also performed set_bnd (colour 1 of the float4 kernel)
     bool rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour, int b) {
@@ -492,7 +549,7 @@ struct CudaExec {
         h.op_offset = op_offset;
         if (lo.present) {
             h.lo_flags = lo.flags;
-            if (bi >= 0) h.lo_plane = lo.base[bi] + g.sz * (lo.nzl - 1);
+            if (bi >= 0) h.lo_plane = lo.base[bi] + g.sz * (lo.nzl - FS_GHOST); // its FS_GHOST top ghost planes
         }
         if (hi.present) {
             h.hi_flags = hi.flags;
@@ -507,8 +564,9 @@ struct CudaExec {
         if (!halo_on) return;
         const unsigned op = ++ops_since_commit;
         const FsHaloArgs h = halo_args(g, field, op);
-        const float *lo_src = field ? field + g.sz * g.kb : nullptr, *hi_src = field ? field + g.sz * (g.ke - 1) : nullptr;
-        const long long plane = g.sz;
+        // FS_GHOST planes each way: my lowest owned planes -> the lower neighbour's top ghosts, my highest -> the upper's bottom ghosts
+        const float *lo_src = field ? field + g.sz * g.kb : nullptr, *hi_src = field ? field + g.sz * (g.ke - FS_GHOST) : nullptr;
+        const long long plane = g.sz * FS_GHOST;
         int blocks = (int)((plane / 4 + 255) / 256);
         if (blocks > sm_count * 2) blocks = sm_count * 2;
         if (blocks < 1 || !field) blocks = 1;

@@ -217,20 +217,50 @@ int64_t fs_launch_count(const fs_solver *s) { return s ? s->core.ex.launches : 0
 int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes) {
     FS_GUARD(s);
     const int kind = kind_and_fill & 15, fill = kind_and_fill >> 4; // fill: 0 as is, 1 random normals, 2 zeros
-    if (reps < 1 || kind < 0 || kind > 2 || fill < 0 || fill > 2 || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    if (reps < 1 || kind < 0 || kind > FS_BENCH_KIND_MAX || fill < 0 || fill > 2 || !fs_valid_b(c, b)) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
     // scratch operands: in = vx0, rhs = vy0, out = tmp (by default whatever the last step left there)
     if (fill == 1) { c.ex.fill_random(c.vx0, c.nloc, 1u); c.ex.fill_random(c.vy0, c.nloc, 2u); }
     if (fill == 2) { c.ex.zero(c.vx0, sizeof(float) * c.nloc); c.ex.zero(c.vy0, sizeof(float) * c.nloc); }
     const long long interior = (long long)(c.g.nx) * c.g.ny * (c.ze - c.zb);
-    // smoother 4 R + 4 W, Jacobi 8 R + 4 W, + 1 flag byte when the grid has obstacles
-    const double per_voxel = (kind == 0 ? 8.0 : 12.0) + (c.fl() ? 1.0 : 0.0);
+    const double fl1 = c.fl() ? 1.0 : 0.0;
+    // SURVEY.md section 8(d), algorithmic bytes per voxel per launch (3D): smoother 4 R + 4 W, Jacobi 8 R + 4 W,
+    // red-black full sweep = one Jacobi sweep's worth, divergence 12 R + 4 W + 4 W (the p = 0 store the reference
+    // makes; this build drops it), gradient 4 R + 24 RW, advect of one scalar 12 R + 4 R + 4 W, fused advect of the
+    // three velocity components 12 R + 12 W (+ the flag byte wherever the grid has obstacles).
+    // Fused pairs: TWO sweeps' worth of algorithmic bytes per launch.
+    double per_voxel = 0.0;
+    switch (kind) {
+    case 0: per_voxel = 8.0 + fl1; break;
+    case 1: case 2: per_voxel = 12.0 + fl1; break;
+    case 3: per_voxel = (c.g.hz ? 20.0 : 16.0) + fl1; break;
+    case 4: per_voxel = (c.g.hz ? 24.0 : 16.0) + fl1; break;
+    case 5: per_voxel = c.g.hz ? 20.0 : 16.0; break;
+    case 6: per_voxel = (c.g.hz ? 28.0 : 20.0) + fl1; break;
+    case 7: per_voxel = 2.0 * (12.0 + fl1); break;
+    case 8: per_voxel = 2.0 * (8.0 + fl1); break;
+    case 9: per_voxel = 12.0 + fl1; break;
+    }
     float a, cc;
     SolverCore<FS_EXEC>::coeffs(c.g.nx, 1e-4f, 0.1f, &a, &cc);
+    const float dt0 = 0.1f * 128.0f / (float)c.g.nx * (float)(c.g.nx - 2);
+    bool ok = true;
     auto once = [&]() {
-        if (kind == 2) { c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0, b); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1, b); }
-        else c.ex.relax(kind == 0 ? FS_MODE_SMOOTH : FS_MODE_JACOBI, c.g, c.vx0, c.vy0, kind == 0 ? c.vx0 : nullptr, c.tmp, c.fl(), a, cc, b, false, true);
+        switch (kind) {
+        case 0: c.ex.relax(FS_MODE_SMOOTH, c.g, c.vx0, c.vy0, c.vx0, c.tmp, c.fl(), a, cc, b, false, true); break;
+        case 1: c.ex.relax(FS_MODE_JACOBI, c.g, c.vx0, c.vy0, nullptr, c.tmp, c.fl(), a, cc, b, false, true); break;
+        case 2: c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 0, b); c.ex.rb_half(c.g, c.tmp, c.vy0, c.fl(), a, cc, 1, b); break;
+        // once-per-step kernels on the live fields (no halo ops: the callers run these on every rank or on none)
+        case 3: c.ex.advect(c.g, c.tmp, c.density, c.vx, c.vy, c.vz, c.fl(), dt0, 0); break;
+        case 4: c.ex.advect_velocity(c.g, c.vx0, c.vy0, c.vz0, c.vx, c.vy, c.vz, c.fl(), dt0); break;
+        case 5: c.ex.divergence(c.g, c.div, c.vx, c.vy, c.vz); break;
+        case 6: c.ex.gradient(c.g, c.vx0, c.vy0, c.vz0, c.pressure, c.fl()); break;
+        case 7: ok = c.ex.relax_pair(FS_PAIR_JACOBI, c.g, c.vx0, c.vy0, c.tmp, c.fl(), a, cc, b, false, true); break;
+        case 8: ok = c.ex.relax_pair(FS_PAIR_SMOOTH, c.g, c.vx0, nullptr, c.tmp, c.fl(), a, cc, b, false, true); break;
+        case 9: ok = c.ex.relax_pair(FS_PAIR_RED_BLACK, c.g, c.vx0, c.vy0, c.tmp, c.fl(), a, cc, b, false, true); break;
+        }
     };
     for (int w = 0; w < 2; w++) once(); // warm-up
+    if (!ok) return c.fail(FS_ERR_UNSUPPORTED, "the fused pair kernel does not support this grid");
     c.ex.timer_start();
     for (int r = 0; r < reps; r++) once();
     const float ms = c.ex.timer_stop();

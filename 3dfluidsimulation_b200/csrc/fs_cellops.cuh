@@ -30,9 +30,16 @@ enum : uint8_t {
 };
 
 enum { FS_MODE_SMOOTH = 0, FS_MODE_JACOBI = 1 };
+// fused two-stage sweeps (fs_kernels.cuh relax_pair): two smoother / Jacobi iterations, or the two colour passes of one
+// red-black sweep, per pass over HBM
+enum { FS_PAIR_SMOOTH = 0, FS_PAIR_JACOBI = 1, FS_PAIR_RED_BLACK = 2 };
+
+// Ghost planes per internal slab side.  Two: a fused two-stage sweep evaluates its first stage one plane beyond the
+// owned range, which reads one plane further; every halo operation moves FS_GHOST planes each way.
+#define FS_GHOST 2
 
 // Geometry of one z-slab.  Local arrays hold planes [zoff, zoff+nzl) of the global grid; the slab
-// owns local planes [kb, ke) and the rest are ghosts filled by the halo exchange.
+// owns local planes [kb, ke) and the rest (FS_GHOST per internal side) are ghosts filled by the halo exchange.
 struct FsGrid {
     int nx, ny, nz;   // GLOBAL dimensions; N ("size") = nx
     int hz;           // nz > 1

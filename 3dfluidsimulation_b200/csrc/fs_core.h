@@ -48,7 +48,7 @@ struct SolverCore {
         if (p.nx < 3 || p.ny < 3 || (p.nz != 1 && p.nz < 3)) return fail(FS_ERR_BAD_ARGUMENT, "nx, ny >= 3 and nz == 1 or nz >= 3 required");
         if (p.iters_diffuse < 0 || p.iters_pressure < 0) return fail(FS_ERR_BAD_ARGUMENT, "negative iteration count");
         if (p.slab_count < 1 || p.slab_rank < 0 || p.slab_rank >= p.slab_count) return fail(FS_ERR_BAD_ARGUMENT, "bad slab_rank/slab_count");
-        if (p.slab_count > 1 && (p.nz == 1 || p.nz / p.slab_count < 2)) return fail(FS_ERR_BAD_ARGUMENT, "z-slabs need nz/slab_count >= 2");
+        if (p.slab_count > 1 && (p.nz == 1 || p.nz / p.slab_count < FS_GHOST)) return fail(FS_ERR_BAD_ARGUMENT, "z-slabs need nz/slab_count >= 2");
         if (p.solver_kind != FS_JACOBI && p.solver_kind != FS_RED_BLACK) return fail(FS_ERR_BAD_ARGUMENT, "unknown solver_kind");
         g.nx = p.nx; g.ny = p.ny; g.nz = p.nz; g.hz = p.nz > 1;
         g.sy = p.nx; g.sz = (long long)p.nx * p.ny;
@@ -56,7 +56,8 @@ struct SolverCore {
         const int P = p.slab_count, r = p.slab_rank;
         zb = (int)((long long)p.nz * r / P);
         ze = (int)((long long)p.nz * (r + 1) / P);
-        const int lo = r > 0 ? zb - 1 : zb, hi = r < P - 1 ? ze + 1 : ze;
+        // FS_GHOST ghost planes per internal side: the fused two-stage sweeps read two planes beyond the owned range
+        const int lo = r > 0 ? zb - FS_GHOST : zb, hi = r < P - 1 ? ze + FS_GHOST : ze;
         g.zoff = lo; g.nzl = hi - lo; g.kb = zb - lo; g.ke = ze - lo;
         nloc = g.sz * g.nzl;
         nowned = g.sz * (ze - zb);
@@ -201,7 +202,7 @@ struct SolverCore {
     // sweep, [halo when the mirror reads z neighbours], mirror, halo.
     void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,
                   bool in_zero) {
-        const bool mir = b != 0 && g_interior_obstacle && (b != 3 || g.hz); // global decision, see g_interior_obstacle
+        const bool mir = needs_mirror(b); // global decision, see g_interior_obstacle
         ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/!mir);
         if (mir) {
             if (b == 3) ex.halo(g, out);
@@ -209,15 +210,31 @@ struct SolverCore {
             ex.halo(g, out);
         }
     }
+    // Whether sweeps of field kind b may be fused in pairs: no obstacle mirroring between the two stages.
+    bool needs_mirror(int b) const { return b != 0 && g_interior_obstacle && (b != 3 || g.hz); }
+    bool pair_ok(int b, float c) const { return !needs_mirror(b) && ex.pair_supported(g, c); }
     // pass 1, DiffuseWithJobs :1292-1357.  Result ends in `x` (roles of x and tmp may swap).
     void smooth(int b, float *&x, const float *x0, float a, float c, int iters) {
         if (iters == 0) { ex.copy(x, x0, sizeof(float) * nloc); return; }
         float *A = tmp, *B = x;
         const float *in = x0;
-        for (int it = 0; it < iters; it++) {
-            float *out = (it & 1) ? B : A;
-            relax_op(FS_MODE_SMOOTH, in, nullptr, it < 2 ? x0 : nullptr, out, a, c, b, false);
+        const bool pairs = pair_ok(b, c);
+        // Obstacle cells keep the stale content of the write buffer (DiffuseJob does not write them, :1055).  Both
+        // reference buffers start as copies of x0 (:1299-1300) and, without mirroring, nothing ever changes those cells:
+        // they hold x0 throughout, so `stale = x0` is exact for every iteration.  With mirroring (b != 0 and interior
+        // obstacles) the stale content is the mirrored value of two iterations ago: x0 for the first two, then the buffer.
+        const bool mir = needs_mirror(b);
+        int sweeps = 0;
+        for (int it = 0; it < iters;) {
+            float *out = (sweeps & 1) ? B : A;
+            if (pairs && it + 2 <= iters && ex.relax_pair(FS_PAIR_SMOOTH, g, in, nullptr, out, fl(), a, c, b, false, true)) {
+                it += 2;
+            } else {
+                relax_op(FS_MODE_SMOOTH, in, nullptr, (!mir || it < 2) ? x0 : nullptr, out, a, c, b, false);
+                it += 1;
+            }
             in = out;
+            sweeps++;
         }
         float *res = const_cast<float *>(in);
         tmp = res == A ? B : A;
@@ -227,14 +244,33 @@ struct SolverCore {
     void lin_solve(int b, float *&x, const float *rhs, float a, float c, int iters, bool zero_guess) {
         if (iters == 0) { if (zero_guess) ex.zero(x, sizeof(float) * nloc); return; }
         float *rd = x, *wr = tmp;
-        for (int it = 0; it < iters; it++) {
-            relax_op(FS_MODE_JACOBI, rd, rhs, nullptr, wr, a, c, b, zero_guess && it == 0);
+        const bool pairs = pair_ok(b, c);
+        for (int it = 0; it < iters;) {
+            const bool iz = zero_guess && it == 0;
+            if (pairs && it + 2 <= iters && ex.relax_pair(FS_PAIR_JACOBI, g, rd, rhs, wr, fl(), a, c, b, iz, true)) {
+                it += 2;
+            } else {
+                relax_op(FS_MODE_JACOBI, rd, rhs, nullptr, wr, a, c, b, iz);
+                it += 1;
+            }
             std::swap(rd, wr);
         }
         x = rd;
         tmp = wr;
     }
-    void lin_solve_rb(int b, float *x, const float *rhs, float a, float c, int iters, bool zero_guess) {
+    // Red-black Gauss-Seidel (BASELINE config 5).  Fused form: both colour passes and set_bnd in one out-of-place pass
+    // (ping-pong like Jacobi).  Fallback: in place, one launch per colour.
+    void lin_solve_rb(int b, float *&x, const float *rhs, float a, float c, int iters, bool zero_guess) {
+        if (pair_ok(b, c) && iters > 0) {
+            float *rd = x, *wr = tmp;
+            for (int it = 0; it < iters; it++) {
+                ex.relax_pair(FS_PAIR_RED_BLACK, g, rd, rhs, wr, fl(), a, c, b, zero_guess && it == 0, true);
+                std::swap(rd, wr);
+            }
+            x = rd;
+            tmp = wr;
+            return;
+        }
         if (zero_guess) {
             ex.zero(x, sizeof(float) * nloc);
             // slabs: a faster neighbour must not store its first boundary plane into this slab's ghost plane before
@@ -262,6 +298,9 @@ struct SolverCore {
     // ---- ProjectWithJobs (FluidSim.cs:1417-1521) ------------------------------------------------
     void project(float *ux, float *uy, float *uz) {
         ex.divergence(g, div, ux, uy, uz);
+        // slabs + fused sweeps: the first stage is evaluated one plane into the ghost zone and reads the right-hand
+        // side there (a single sweep only reads div on owned planes)
+        if (pair_ok(0, 6.0f)) ex.halo(g, div);
         if (prm.solver_kind == FS_RED_BLACK)
             lin_solve_rb(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true);
         else

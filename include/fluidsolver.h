@@ -178,10 +178,15 @@ int fs_op_enforce_obstacles(fs_solver *s);
 int fs_timer_start(fs_solver *s);
 int fs_timer_stop(fs_solver *s, float *elapsed_ms); /* records, synchronises, returns the interval */
 int64_t fs_launch_count(const fs_solver *s);        /* kernels launched by this handle so far */
-/* Average duration of `reps` back-to-back launches of one relaxation sweep on the scratch fields
- * (in = VX0, rhs = VY0).  kind_and_fill = kind + 16*fill; kind 0 = pass-1 smoother, 1 = Jacobi,
- * 2 = red-black full sweep; fill 0 = operands as the last step left them, 1 = overwrite them with
- * uniform random normals first, 2 = zeros.  Also returns the algorithmic bytes per launch. */
+/* Average duration of `reps` back-to-back launches of one kernel of the step, for the roofline figures.
+ * kind_and_fill = kind + 16*fill.  Relaxation sweeps on the scratch fields (in = VX0, rhs = VY0, out = ping-pong):
+ *   0 pass-1 smoother, 1 Jacobi, 2 red-black full sweep as two colour launches,
+ *   7 fused Jacobi pair (two iterations per launch), 8 fused smoother pair, 9 fused red-black full sweep;
+ * once-per-step kernels on the live fields (call them after the timed steps; scratch fields are overwritten):
+ *   3 advect of one scalar (density), 4 fused advect of the velocity components, 5 divergence, 6 gradient subtract.
+ * fill 0 = operands as the last step left them, 1 = overwrite the sweep operands with uniform random numbers first,
+ * 2 = zeros.  Also returns the algorithmic bytes per launch (SURVEY.md section 8d per-voxel figures x owned voxels). */
+#define FS_BENCH_KIND_MAX 9
 int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps, float *avg_ms, double *algo_bytes);
 
 /* Self-test of the sweep kernels' constant-divisor division (csrc/fs_kernels.cuh fs_div) against IEEE

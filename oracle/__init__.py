@@ -25,7 +25,7 @@ _U8 = C.POINTER(C.c_uint8)
 
 def build(force: bool = False) -> str:
     """Compile oracle/*.c with gcc (see oracle/Makefile). Returns the .so path."""
-    srcs = [os.path.join(_HERE, f) for f in ("fluid_oracle.c", "ref2d.c", "fluid_oracle.h", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("fluid_oracle.c", "ref2d.c", "ref_faithful3d.c", "fluid_oracle.h", "Makefile")]
     stale = (not os.path.exists(_SO)) or any(os.path.getmtime(s) > os.path.getmtime(_SO) for s in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B", "-s"], check=True)
@@ -222,9 +222,15 @@ class OracleSolver:
             if a is not None:
                 self.f[n] += a.astype(np.float32).reshape(self.shape)
 
-    def step(self, dt, visc, diff):
+    def step(self, dt, visc, diff, faithful=False):
+        """One Simulate().  faithful=True runs ref_faithful3d.c: same bits, the reference's execution structure
+        (static-64 job batches, single-threaded BoundaryJob scans, per-call allocate-and-copy; Jacobi only)."""
         s = self._state()
-        lib().fo_step(C.byref(s), _cf(dt), _cf(visc), _cf(diff))
+        if faithful:
+            assert not self.red_black, "the reference has no red-black solver"
+            lib().rf_step(C.byref(s), _cf(dt), _cf(visc), _cf(diff))
+        else:
+            lib().fo_step(C.byref(s), _cf(dt), _cf(visc), _cf(diff))
 
     def metrics(self):
         s = self._state()

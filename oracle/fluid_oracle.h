@@ -59,6 +59,9 @@ void fo_enforce_obstacles(int nx, int ny, int nz, float *vx, float *vy, float *v
                           float cell, float rawvisc);
 long long fo_cell_index(int nx, int ny, int nz, float x, float y, float z);
 void fo_step(fo_state *s, float dt, float visc, float diff);
+/* Same step, same bits, with the reference's EXECUTION structure (flat static-64 job loops, single-threaded
+ * boundary scans, per-call allocate-and-copy): ref_faithful3d.c, the "port-faithful" CPU baseline. */
+void rf_step(fo_state *s, float dt, float visc, float diff);
 void fo_metrics(const fo_state *s, float *mean_density, float *max_speed);
 
 /* literal 2D restatement (ref2d.c) */

@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <thread>
@@ -61,6 +62,61 @@ struct HostExec {
         else
             cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         if (fuse_halo) halo(g, out);
+    }
+    // Fused two-stage sweep, emulated with the per-cell functions and LOCAL data only (so that the CPU tier checks the
+    // two-plane halo logic): stage 1 on the owned interior planes plus one plane each side into a scratch copy of
+    // `in`, stage 2 on the owned interior planes.  FS_EMUL_NO_PAIR=1 makes the orchestration fall back to single sweeps.
+    bool pair_supported(const FsGrid &g, float) const {
+        const char *e = getenv("FS_EMUL_NO_PAIR");
+        return g.hz && !(e && e[0] == '1');
+    }
+    template <class F>
+    void cells_range(const FsGrid &g, int klo, int khi, F f) { // interior rows / columns of local planes [klo, khi)
+        for (int kl = khi - 1; kl >= klo; kl--)
+            for (int j = g.ny - 2; j >= 1; j--)
+                for (int i = g.nx - 2; i >= 1; i--) f(i, j, kl);
+    }
+    bool relax_pair(int kind, const FsGrid &g, const float *in, const float *rhs, float *out, const uint8_t *flags,
+                    float a, float c, int b, bool in_zero, bool fuse_halo) {
+        if (!pair_supported(g, c)) return false;
+        const int zb = g.zoff + g.kb, ze = g.zoff + g.ke;
+        const int k0 = (zb < 1 ? 1 : zb) - g.zoff, k1 = (ze > g.nz - 1 ? g.nz - 1 : ze) - g.zoff; // owned interior [k0, k1)
+        if (k1 <= k0) return true;
+        const long long n = g.sz * g.nzl;
+        std::vector<float> y(n);
+        if (in_zero) std::fill(y.begin(), y.end(), 0.0f); else memcpy(y.data(), in, sizeof(float) * n);
+        const float *src = in_zero ? nullptr : in;
+        std::vector<float> zeros;
+        if (in_zero) { zeros.assign(n, 0.0f); src = zeros.data(); }
+        // stage 1 range: one plane beyond the owned interior planes where that plane is itself interior
+        const int s0 = (k0 - 1 + g.zoff >= 1) ? k0 - 1 : k0, s1 = (k1 + g.zoff <= g.nz - 2) ? k1 + 1 : k1;
+        if (kind == FS_PAIR_RED_BLACK) {
+            cells_range(g, s0, s1, [&](int i, int j, int kl) {
+                if (((i + j + kl + g.zoff) & 1) == 0) fs_rb_cell(g, y.data(), rhs, flags, a, c, i, j, kl);
+            });
+            // owned planes only: a faster neighbour may already be storing its planes of this op into out's ghosts.
+            // A colour-1 cell has colour-0 neighbours only, which stage 2 does not change: read them from y.
+            memcpy(out + g.sz * g.kb, y.data() + g.sz * g.kb, sizeof(float) * g.sz * (g.ke - g.kb));
+            cells_range(g, k0, k1, [&](int i, int j, int kl) {
+                const long long idx = fs_idx(g, i, j, kl);
+                if (((i + j + kl + g.zoff) & 1) != 1 || (flags && (flags[idx] & FS_OB_SELF))) return;
+                const float *x = y.data();
+                float s = ((x[idx + 1] + x[idx - 1]) + x[idx + g.sy]) + x[idx - g.sy];
+                s = (s + x[idx + g.sz]) + x[idx - g.sz];
+                out[idx] = (rhs[idx] + a * s) / c;
+            });
+            cells_range(g, k0, k1, [&](int i, int j, int kl) { fs_bnd_cell(g, out, b, i, j, kl); });
+        } else if (kind == FS_PAIR_JACOBI) {
+            cells_range(g, s0, s1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, src, rhs, nullptr, y.data(), flags, a, c, b, false, i, j, kl); });
+            cells_range(g, k0, k1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, y.data(), rhs, nullptr, out, flags, a, c, b, false, i, j, kl); });
+        } else {
+            cells_range(g, s0, s1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, src, nullptr, src, y.data(), flags, a, c, b, false, i, j, kl); });
+            std::vector<float> y2(y); // obstacle cells copy the stage's input
+            cells_range(g, k0, k1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, y.data(), nullptr, y2.data(), out, flags, a, c, b, false, i, j, kl); });
+        }
+        launches++;
+        if (fuse_halo) halo(g, out);
+        return true;
     }
     bool rb_half(const FsGrid &g, float *x, const float *rhs, const uint8_t *flags, float a, float c, int colour, int /*b*/) {
         cells(g, [&](int i, int j, int kl) {
@@ -174,8 +230,8 @@ struct HostExec {
         if (hi.present) spin(hi.seq, op - 1);
         const int bi = field ? buf_index(field) : -1;
         if (bi >= 0) {
-            if (lo.present) memcpy(lo.base[bi] + g.sz * (lo.nzl - 1), field + g.sz * g.kb, sizeof(float) * g.sz);
-            if (hi.present) memcpy(hi.base[bi], field + g.sz * (g.ke - 1), sizeof(float) * g.sz);
+            if (lo.present) memcpy(lo.base[bi] + g.sz * (lo.nzl - FS_GHOST), field + g.sz * g.kb, sizeof(float) * g.sz * FS_GHOST);
+            if (hi.present) memcpy(hi.base[bi], field + g.sz * (g.ke - FS_GHOST), sizeof(float) * g.sz * FS_GHOST);
         }
         my_seq->store(op, std::memory_order_release);
         if (lo.present) spin(lo.seq, op);

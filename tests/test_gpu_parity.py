@@ -211,8 +211,9 @@ def test_red_black_matches_oracle(lib, oracle):
 def test_vector_and_scalar_kernels_agree(lib, oracle):
     """relax_vec4 against the per-cell kernels (FS_FORCE_GENERIC=1) on a grid the oracle would take
     minutes for: 256^3, full step, bit-identical fields."""
-    def run(force):
+    def run(force, no_pair=False):
         os.environ["FS_FORCE_GENERIC"] = "1" if force else "0"
+        os.environ["FS_NO_PAIR"] = "1" if no_pair else "0"
         try:
             s, _ = None, None
             pk = P.pkg()
@@ -227,9 +228,39 @@ def test_vector_and_scalar_kernels_agree(lib, oracle):
             return out
         finally:
             os.environ.pop("FS_FORCE_GENERIC", None)
-    a, b = run(False), run(True)
+            os.environ.pop("FS_NO_PAIR", None)
+    a, b, c = run(False), run(True), run(False, no_pair=True)
     for n in a:
-        P.assert_exact(a[n], b[n], f"vec4 vs per-cell {n}")
+        P.assert_exact(a[n], b[n], f"fused/vec4 vs per-cell {n}")
+        P.assert_exact(a[n], c[n], f"fused two-stage sweeps vs single vec4 sweeps {n}")
+
+
+@pytest.mark.parametrize("kind", ["jacobi", "smooth", "rb"])
+@pytest.mark.parametrize("dims", [(64, 40, 35), (132, 20, 70), (8, 3, 3), (4, 3, 3), (256, 100, 9), (16, 12, 9)])
+def test_fused_pair_kernel_vs_oracle(lib, oracle, kind, dims):
+    """The fused two-stage sweep (two Jacobi / smoother iterations or both red-black colours per pass) against the
+    oracle for every field kind b it is used for (b = 0 with obstacles; b = 1, 2, 3 without), odd iteration counts
+    (pair + single mix) and tile shapes that leave partial tiles in x, y and z."""
+    nx, ny, nz = dims
+    rng = np.random.default_rng(5)
+    shape = (nz, ny, nx)
+    x0, guess = P.rnd(shape, rng), P.rnd(shape, rng)
+    a, c = np.float32(0.37), np.float32(1 + 6 * 0.37)
+    for obstacles, bs in ((True, (0,)), (False, (0, 1, 2, 3))):
+        mask = P.random_mask(shape, rng) if obstacles else np.zeros(shape, np.uint8)
+        with P.make_solver(lib, nx, ny, nz) as s:
+            s.set_obstacles(mask)
+            for b in bs:
+                for it in (2, 3, 6, 7):
+                    s.set_field("vx", x0); s.set_field("vy0", guess); s.set_field("vx0", P.rnd(shape, rng))
+                    if kind == "smooth":
+                        s.op_smooth("vx0", "vx", b, a, c, it)
+                        P.assert_exact(s.get_field("vx0"), oracle.diffuse_smooth(b, x0, a, c, mask, it), f"pair smooth b={b} it={it}")
+                    else:
+                        rb = kind == "rb"
+                        s.op_lin_solve("vy0", "vx", b, a, c, it, solver_kind=1 if rb else 0)
+                        P.assert_exact(s.get_field("vy0"), oracle.lin_solve(b, guess, x0, a, c, mask, it, red_black=rb),
+                                       f"pair {kind} b={b} it={it}")
 
 
 def test_full_size_properties_512(lib):
