@@ -1,24 +1,34 @@
 #!/usr/bin/env python
 """bench.py -- throughput of the stable-fluids step (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 512|1024|256|128] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload 512|1024|1024rb|256|128|32]
+                    [--scaling strong|weak] [--impl reference]
 
 A "step" is one full Simulate() (velocity step + density step + obstacle pass) over the whole grid,
 preceded -- as in the reference's Update() -- by the smoke-plume source injection.
 Workload (default): BASELINE.json configs[3], the configuration the metric ("... at 1/2/4/8 GPUs") is
 quoted on: 512^3, K_d = 20, K_p = 80 Jacobi, dt = 0.1*128/N, obstacle sphere r = 0.1N, z-slabs across
-the N GPUs (strong scaling: the grid is fixed).  The state (6 GB) is far larger than L2, so no
-explicit L2 flush is needed between timed steps.
+the N GPUs (strong scaling: the grid is fixed; --scaling weak keeps 512 x 512 x 512 per GPU instead).
+The state (6 GB) is far larger than L2, so no explicit L2 flush is needed between timed steps.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      dominant kernel = the 3D Jacobi sweep (relax_vec4): algorithmic 13 B/voxel (12 without
-                obstacles: no flag stream) * voxels per launch / average launch duration (CUDA events on the
-                solver's stream, 20 back-to-back launches on the live fields in this process right after the
-                timed steps), against MEASURED_PEAKS.json hbm_gbs; traffic = ncu dram bytes (profiles/).
-  cpu_baseline  the CPU oracle (C restatement of FluidSim.cs, OpenMP) on a bounded sample (rank 0, N=1)
-  e2e           same metric through the C ABI with HOST buffers: per step the source cells go host->
-                device and density + pressure (what UpdateVisualization reads, FluidSim.cs:761-768)
-                come back into pinned host memory.
+  roofline      the kernel with the largest share of the step (the fused two-stage Jacobi sweep when the grid takes
+                it, else the single Jacobi sweep): COMPULSORY bytes per launch (in 4 + rhs 4 + flags 1 + out 4 =
+                13 B/voxel) / average launch duration (CUDA events on the solver's stream, back-to-back launches on
+                the live fields right after the timed steps) against MEASURED_PEAKS.json hbm_gbs; `kernels` lists
+                the same figure for every kernel of the step; traffic = ncu dram bytes (profiles/).
+  cpu_baseline  the CPU oracle (C restatement of FluidSim.cs, OpenMP, all host cores) on a bounded sample: a
+                z-slab of the SAME nx x ny grid (same rows, same coefficients) with 256^3 voxels' worth of planes;
+                "port-tidy" = oracle/fluid_oracle.c, "port-faithful" = oracle/ref_faithful3d.c (static-64 job
+                batches, serial BoundaryJob scans, per-call allocate-and-copy, as FluidSim.cs executes).
+  e2e           same metric through the C ABI with HOST buffers: per step the source cells go host->device and
+                density + pressure (what UpdateVisualization reads, FluidSim.cs:761-768) come back into pinned host
+                memory; frame_value = the drop-in's frame instead (sources, fs_step, fs_render_rgba of the mid
+                plane + fs_get_metrics: 4 MB instead of 1 GB of readback).
+  parity_check  (N > 1) before timing, a small slab case over the same N ranks is compared bit for bit with a
+                1-GPU handle on rank 0.
+  extra         short 1024^3 K_p = 100 runs (BASELINE configs[4]: Jacobi and red-black, strong scaling) and the
+                weak-scaling variant 1024 x 1024 x 128 per GPU.
 """
 from __future__ import annotations
 
@@ -37,34 +47,46 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (n, K_d, K_p, solver_kind, BASELINE.json config)
+    "32": (32, 20, 20, 0, "configs[0]: 32^3, K_d=K_p=20"),
     "128": (128, 20, 40, 0, "configs[1]: 128^3, K_p=40"),
     "256": (256, 20, 20, 0, "configs[2]: 256^3 via the C ABI"),
     "512": (512, 20, 80, 0, "configs[3]: 512^3, K_p=80, z-slabs at 1/2/4/8 GPUs"),
     "1024": (1024, 20, 100, 0, "configs[4] grid with Jacobi: 1024^3, K_p=100"),
     "1024rb": (1024, 20, 100, 1, "configs[4]: 1024^3, K_p=100 red-black"),
 }
+METRIC = "Gvoxel-updates/s per full fluid step"
 
 
 def step_bytes_per_voxel(kd, kp):
     return 88 * kd + 26 * kp + 182  # SURVEY.md section 8(d) / BASELINE.md section 3
 
 
-def plume(n, nz):
-    """Smoke-plume source cells: ball at (0.5N, 0.2N, 0.5N), r = max(1.5, N/16),
+def plume(nx, ny, nz):
+    """Smoke-plume source cells: ball at (0.5 nx, 0.2 ny, 0.5 nz), r = max(1.5, nx/16),
     density +100*falloff, upward (+y) velocity v_src*falloff with CFL = dt*(N-2)*v_src ~ 2.5."""
-    sx, sy, sz, rad = 0.5 * n, 0.2 * n, 0.5 * nz, max(1.5, n / 16)
+    sx, sy, sz, rad = 0.5 * nx, 0.2 * ny, 0.5 * nz, max(1.5, nx / 16)
     r = int(np.ceil(rad)) + 1
-    ii, jj, kk = np.meshgrid(np.arange(int(sx) - r, int(sx) + r + 1), np.arange(int(sy) - r, int(sy) + r + 1),
-                             np.arange(int(sz) - r, int(sz) + r + 1), indexing="ij")
+    ks = np.arange(max(int(sz) - r, 0), min(int(sz) + r, nz - 1) + 1)
+    js = np.arange(max(int(sy) - r, 0), min(int(sy) + r, ny - 1) + 1)
+    is_ = np.arange(max(int(sx) - r, 0), min(int(sx) + r, nx - 1) + 1)
+    kk, jj, ii = np.meshgrid(ks, js, is_, indexing="ij")
     d = np.sqrt((ii - sx) ** 2 + (jj - sy) ** 2 + (kk - sz) ** 2)
     keep = d <= rad
     fall = (1.0 - d[keep] / rad).astype(np.float32)
     return (ii[keep].astype(np.float32), jj[keep].astype(np.float32), kk[keep].astype(np.float32), fall)
 
 
-def sphere_mask(n, nz):
-    z, y, x = np.ogrid[:nz, :n, :n]
-    return (((x - 0.5 * n) ** 2 + (y - 0.5 * n) ** 2 + (z - 0.5 * nz) ** 2) < (0.1 * n) ** 2).astype(np.uint8)
+def sphere_mask(nx, ny, nz):
+    """Obstacle sphere r = 0.1 nx at the centre, built plane by plane (no nx*ny*nz float temporaries at 1024^3)."""
+    y, x = np.ogrid[:ny, :nx]
+    d2 = (x - 0.5 * nx) ** 2 + (y - 0.5 * ny) ** 2
+    m = np.zeros((nz, ny, nx), np.uint8)
+    r2 = (0.1 * nx) ** 2
+    for k in range(nz):
+        dz2 = (k - 0.5 * nz) ** 2
+        if dz2 < r2:
+            m[k] = d2 + dz2 < r2
+    return m
 
 
 class ClockSampler(threading.Thread):
@@ -140,23 +162,33 @@ def ncu_traffic(kernel):
     return None
 
 
-# ---------------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(n, kd, kp, steps, warmup=1):
-    """Times the CPU oracle (OpenMP over all host cores) on an n^3 sample of the workload."""
+# ---- CPU arm ---------------------------------------------------------------------------------------------
+def cpu_sample_dims(n):
+    """Bounded sample of the n^3 workload for the CPU arm: the whole grid up to 256^3, else a z-slab of the same
+    nx x ny grid holding 256^3 voxels (512 -> 512x512x64, 1024 -> 1024x1024x16): same row length, same plane size,
+    same coefficients (N = nx), the per-voxel work of the full grid."""
+    if n <= 256:
+        return n, n, n
+    return n, n, max(256 ** 3 // (n * n), 8)
+
+
+def cpu_oracle_rate(dims, kd, kp, steps, warmup=1, faithful=False):
+    """Times the CPU oracle (OpenMP over all host cores) on an nx x ny x nz sample of the workload."""
     import oracle
 
     oracle.set_threads(os.cpu_count())  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
-    o = oracle.OracleSolver(n, n, n, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=True, cell_size=1.0 / n)
-    o.obstacles[...] = sphere_mask(n, n)
-    x, y, z, fall = plume(n, n)
-    dt = 0.1 * 128 / n
-    vsrc = 2.5 / (dt * (n - 2))
+    nx, ny, nz = dims
+    o = oracle.OracleSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, enable_obstacle=True, cell_size=1.0 / nx)
+    o.obstacles[...] = sphere_mask(nx, ny, nz)
+    x, y, z, fall = plume(nx, ny, nz)
+    dt = 0.1 * 128 / nx
+    vsrc = 2.5 / (dt * (nx - 2))
+    idx = (z.astype(np.int64) * ny + y.astype(np.int64)) * nx + x.astype(np.int64)
 
     def one():
-        idx = (z.astype(np.int64) * n + y.astype(np.int64)) * n + x.astype(np.int64)
         o.f["density"].reshape(-1)[idx] += np.float32(100) * fall
         o.f["vy"].reshape(-1)[idx] += np.float32(vsrc) * fall
-        o.step(dt, 1e-4, 1e-4)
+        o.step(dt, 1e-4, 1e-4, faithful=faithful)
 
     for _ in range(warmup):
         one()
@@ -164,7 +196,22 @@ def cpu_oracle_rate(n, kd, kp, steps, warmup=1):
     for _ in range(steps):
         one()
     dtm = time.perf_counter() - t0
-    return n ** 3 * steps / dtm / 1e9, dtm / steps * 1e3
+    return nx * ny * nz * steps / dtm / 1e9, dtm / steps * 1e3
+
+
+def cpu_baseline_block(n, kd, kp, steps, warmup, faithful_steps=2):
+    dims = cpu_sample_dims(n)
+    val, ms = cpu_oracle_rate(dims, kd, kp, steps, warmup)
+    fval, fms = cpu_oracle_rate(dims, kd, kp, faithful_steps, 1, faithful=True)
+    sample = f"{dims[0]}x{dims[1]}x{dims[2]} voxels" + ("" if dims[2] == n else f" (z-slab of the {n}^3 grid, same rows/planes/coefficients)")
+    return dims, {
+        "value": val, "unit": "Gvoxel-updates/s", "cores": os.cpu_count(), "kind": "port-tidy",
+        "sample": f"{sample}, same K_d/K_p, {steps} steps after {warmup} warm-up ({ms:.0f} ms/step); oracle/fluid_oracle.c, OpenMP over planes",
+        "faithful": {"value": fval, "unit": "Gvoxel-updates/s", "cores": os.cpu_count(), "kind": "port-faithful",
+                     "sample": f"{sample}, {faithful_steps} steps after 1 warm-up ({fms:.0f} ms/step); oracle/ref_faithful3d.c: "
+                               "static-64 job batches, single-threaded BoundaryJob scan after every sweep, per-call allocate-and-copy "
+                               "(FluidSim.cs:1299-1301, :1324, :1645)"},
+    }
 
 
 def run_reference(args):
@@ -172,33 +219,157 @@ def run_reference(args):
     if rank != 0:
         return
     n, kd, kp, kind, cfg = WORKLOADS[args.workload]
-    sample = 128 if n >= 128 else n
-    cores = os.cpu_count()
-    val, ms = cpu_oracle_rate(sample, kd, kp, args.steps, max(args.warmup, 1))
+    warm = max(args.warmup, 1)
+    dims, block = cpu_baseline_block(n, kd, kp, args.steps, warm)
+    val = block["value"]
     line = {
-        "impl": "reference", "metric": "Gvoxel-updates/s per full fluid step", "value": val, "unit": "Gvoxel-updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg, "grid": [n, n, n], "iters_diffuse": kd, "iters_pressure": kp, "solver": "jacobi",
-                   "note": "reference C# cannot run here (no dotnet/mono/Unity); this arm times the CPU oracle, a C restatement of FluidSim.cs"},
-        "cpu_baseline": {"value": val, "unit": "Gvoxel-updates/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample}^3 sub-grid of the workload, same K_d/K_p, {args.steps} steps after {max(args.warmup, 1)} warm-up"},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "Gvoxel-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": warm, "ms_per_step": dims[0] * dims[1] * dims[2] / val / 1e6,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg, "grid": list(dims), "workload_grid": [n, n, n], "iters_diffuse": kd, "iters_pressure": kp,
+                   "solver": "jacobi", "dt": 0.1 * 128 / n, "obstacle": "sphere r=0.1N",
+                   "note": "reference C# cannot run here (no dotnet/mono/Unity); this arm times the CPU oracle, a C restatement of "
+                           "FluidSim.cs, on `grid` (a bounded sample of `workload_grid`); per-voxel rate"},
+        "cpu_baseline": block,
         "e2e": {"value": val, "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
-# ---------------------------------------------------------------------------------------------------------
+# ---- GPU arm -----------------------------------------------------------------------------------------------
+class Job:
+    """Process-group plumbing shared by the timed runs (one process per GPU)."""
+
+    def __init__(self, torch, dist, rank, world, local):
+        self.torch, self.dist, self.rank, self.world, self.local = torch, dist, rank, world, local
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def connect(self, s):
+        if self.world > 1:
+            blobs = [None] * self.world
+            self.dist.all_gather_object(blobs, s.halo_export())
+            s.halo_connect(blobs[self.rank - 1] if self.rank > 0 else None,
+                           blobs[self.rank + 1] if self.rank < self.world - 1 else None)
+            self.dist.barrier()
+
+
+def make_plume_solver(pkg, job, lib, dims, kd, kp, kind, obstacle, graph):
+    nx, ny, nz = dims
+    s = pkg.NativeSolver(nx, ny, nz, iters_diffuse=kd, iters_pressure=kp, solver_kind=kind, enable_obstacle=obstacle,
+                         cell_size=1.0 / nx, device_id=job.local, slab_rank=job.rank, slab_count=job.world,
+                         use_cuda_graph=graph, lib_path=lib)
+    job.connect(s)
+    if obstacle:
+        s.set_obstacles(sphere_mask(nx, ny, nz))
+    px, py, pz, fall = plume(nx, ny, nz)
+    dt = 0.1 * 128 / nx
+    vsrc = 2.5 / (dt * (nx - 2))
+    dens_amt, vy_amt = (np.float32(100) * fall), (np.float32(vsrc) * fall)
+
+    def one_step():
+        s.add_source_cells(px, py, pz, density=dens_amt, ay=vy_amt)
+        s.step(dt, 1e-4, 1e-4)
+
+    return s, one_step, px.size
+
+
+def timed_run(job, s, one_step, steps, warmup, sample_clocks=False):
+    for _ in range(warmup):
+        one_step()
+    s.sync()
+    sampler = ClockSampler(job.local) if sample_clocks else None
+    job.barrier()
+    if sampler:
+        sampler.start()
+    l0 = s.launch_count()
+    s.timer_start()
+    for _ in range(steps):
+        one_step()
+    ms = s.timer_stop()
+    launches = s.launch_count() - l0
+    job.barrier()
+    clocks = sampler.result() if sampler else None
+    return job.max_over_ranks(ms), launches, clocks
+
+
+def parity_check(pkg, job, lib):
+    """Slab correctness inside the benchmark job: 64 x 40 x 48, obstacles, K_d = 6, K_p = 8,
+    3 steps with the CUDA graph, on the same `world` ranks / GPUs as the timed run; rank 0 repeats it on one GPU with
+    a single handle and compares every owned plane of every rank bit for bit."""
+    nx, ny, nz, steps = 64, 40, 48, 3
+    rng = np.random.default_rng(5)
+    shape = (nz, ny, nx)
+    mask = (rng.random(shape) < 0.04).astype(np.uint8)
+    fields = {n: ((rng.random(shape, dtype=np.float32) * 2 - 1) * np.float32(2.0)).astype(np.float32) for n in ("density", "vx", "vy", "vz")}
+    kw = dict(iters_diffuse=6, iters_pressure=8, enable_obstacle=True, cell_size=1.0 / nx, use_cuda_graph=True, lib_path=lib)
+    out = {"ranks": job.world, "grid": [nx, ny, nz], "steps": steps, "solvers": {}}
+    ok_all = True
+    for kind, name in ((0, "jacobi"), (1, "red-black")):
+        s = pkg.NativeSolver(nx, ny, nz, device_id=job.local, slab_rank=job.rank, slab_count=job.world, solver_kind=kind, **kw)
+        job.connect(s)
+        s.set_obstacles(mask)
+        for n, a in fields.items():
+            s.set_field(n, a[s.z_begin:s.z_end])
+        for _ in range(steps):
+            s.step(0.05, 3e-3, 2e-3)
+        mine = {n: s.get_field(n) for n in ("density", "vx", "vy", "vz", "pressure")}
+        s.close()
+        parts = [None] * job.world
+        job.dist.all_gather_object(parts, mine)
+        if job.rank == 0:
+            ref = pkg.NativeSolver(nx, ny, nz, device_id=job.local, solver_kind=kind, **kw)
+            ref.set_obstacles(mask)
+            for n, a in fields.items():
+                ref.set_field(n, a)
+            for _ in range(steps):
+                ref.step(0.05, 3e-3, 2e-3)
+            exact = True
+            for n in mine:
+                got = np.concatenate([p[n] for p in parts], axis=0)
+                exact = exact and bool(np.array_equal(got, ref.get_field(n)))
+            ref.close()
+            out["solvers"][name] = exact
+            ok_all = ok_all and exact
+    out["bit_exact"] = ok_all
+    return out
+
+
+def short_run(pkg, job, lib, dims, kd, kp, kind, steps, warmup, graph=True):
+    s, one_step, _ = make_plume_solver(pkg, job, lib, dims, kd, kp, kind, True, graph)
+    try:
+        ms, launches, _ = timed_run(job, s, one_step, steps, warmup)
+        vox = dims[0] * dims[1] * dims[2]
+        return {"grid": list(dims), "iters_diffuse": kd, "iters_pressure": kp, "solver": "red-black" if kind else "jacobi",
+                "steps": steps, "warmup": warmup, "ms_per_step": ms / steps, "value": vox * steps / (ms * 1e-3) / 1e9,
+                "unit": "Gvoxel-updates/s", "n_gpus": job.world, "gpu_launches": int(launches)}
+    finally:
+        s.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default="512", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-obstacle", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the 1024^3 / weak-scaling side measurements")
+    ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline list")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -217,63 +388,31 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    job = Job(torch, dist, rank, world, local)
 
     pkg = importlib.import_module("3dfluidsimulation_b200")
     bld = importlib.import_module("3dfluidsimulation_b200.build")
-    lib = bld.build()
+    if local == 0:
+        lib = bld.build()          # one builder per node (atomic rename inside); the others wait and load
+    if world > 1:
+        dist.barrier()
+    lib = bld.LIB
     n, kd, kp, kind, cfg = WORKLOADS[args.workload]
     warmup = max(args.warmup, 3)
-    dt = 0.1 * 128 / n
-    vsrc = 2.5 / (dt * (n - 2))
     obstacle = not args.no_obstacle
+    graph = not args.no_graph
+    dims = (n, n, n * world) if args.scaling == "weak" else (n, n, n)
+    voxels = dims[0] * dims[1] * dims[2]
 
-    s = pkg.NativeSolver(n, n, n, iters_diffuse=kd, iters_pressure=kp, solver_kind=kind, enable_obstacle=obstacle,
-                         cell_size=1.0 / n, device_id=local, slab_rank=rank, slab_count=world,
-                         use_cuda_graph=not args.no_graph, lib_path=lib)
-    if world > 1:
-        blobs = [None] * world
-        dist.all_gather_object(blobs, s.halo_export())
-        s.halo_connect(blobs[rank - 1] if rank > 0 else None, blobs[rank + 1] if rank < world - 1 else None)
-        dist.barrier()
-    if obstacle:
-        s.set_obstacles(sphere_mask(n, n))
-    px, py, pz, fall = plume(n, n)
-    dens_amt, vy_amt = (np.float32(100) * fall), (np.float32(vsrc) * fall)
-    h2d_bytes = px.size * (8 + 4 * 2)  # what fs_add_source_cells uploads: int64 index + 2 amounts per cell
+    check = parity_check(pkg, job, lib) if world > 1 else None
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def one_step():
-        s.add_source_cells(px, py, pz, density=dens_amt, ay=vy_amt)
-        s.step(dt, 1e-4, 1e-4)
+    s, one_step, ncells = make_plume_solver(pkg, job, lib, dims, kd, kp, kind, obstacle, graph)
+    h2d_bytes = ncells * (8 + 4 * 2)  # what fs_add_source_cells uploads: int64 index + 2 amounts per cell
+    dt = 0.1 * 128 / n
 
     # ---- device-resident throughput ----------------------------------------------------------------------
-    for _ in range(warmup):
-        one_step()
-    s.sync()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    l0 = s.launch_count()
-    s.timer_start()
-    for _ in range(args.steps):
-        one_step()
-    ms = s.timer_stop()
-    launches = s.launch_count() - l0
-    barrier()
-    clocks = sampler.result()
-    ms = max_over_ranks(ms)
-    value = n ** 3 * args.steps / (ms * 1e-3) / 1e9
+    ms, launches, clocks = timed_run(job, s, one_step, args.steps, warmup, sample_clocks=True)
+    value = voxels * args.steps / (ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
     # Every step: source cells host->device, fs_step, then density + pressure device->host into pinned buffers.
@@ -282,7 +421,7 @@ def main():
     # set t+1 is in flight.  The timed region ends only when the last transfer has landed (fs_wait_transfers).
     host = [[torch.empty(s.shape, dtype=torch.float32, pin_memory=True).numpy() for _ in range(2)] for _ in range(2)]
     one_step(); s.get_field_async("density", host[0][0]); s.get_field_async("pressure", host[0][1]); s.wait_transfers()
-    barrier()
+    job.barrier()
     t0 = time.perf_counter()
     for it in range(args.steps):
         one_step()
@@ -290,63 +429,129 @@ def main():
         s.get_field_async("pressure", host[it & 1][1])
     s.wait_transfers()
     s.sync()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = n ** 3 * args.steps / e2e_s / 1e9
+    e2e_s = job.max_over_ranks(time.perf_counter() - t0)
+    e2e_value = voxels * args.steps / e2e_s / 1e9
     d2h_bytes = int(host[0][0].nbytes + host[0][1].nbytes)
-    # the same loop with the blocking fs_get_field, for comparison
+    # the drop-in's frame: Update() = sources, Simulate(), UpdateVisualization() (colour mapping on the device, one
+    # RGBA plane back) and LogCurrentMetrics() (two reductions back) -- FluidSim.cs:390-450, :755-866, :578-607
+    vis = pkg.native.FsVisParams.reference_defaults(n, 2)
+    vis.z_slice = dims[2] // 2
+    renders = s.z_begin <= vis.z_slice < s.z_end
+    rgba = np.empty((dims[1], dims[0], 4), np.float32)
+    job.barrier()
     t0 = time.perf_counter()
     for it in range(args.steps):
         one_step()
-        s.get_field("density", host[0][0])
-        s.get_field("pressure", host[0][1])
-    e2e_blocking_s = max_over_ranks(time.perf_counter() - t0)
+        if renders:
+            s.render_rgba(vis, rgba)
+        s.metrics()
+    s.sync()
+    frame_s = job.max_over_ranks(time.perf_counter() - t0)
+    del host
 
-    # ---- roofline of the dominant kernel (3D Jacobi sweep), live, CUDA events on the solver stream ------------
+    # ---- roofline of the step's kernels, live, CUDA events on the solver stream --------------------------------
     peak, peak_src = measured_peak()
-    sweep_ms, sweep_bytes = s.bench_sweep(1, 0, 20)
-    sweep_ms = max_over_ranks(sweep_ms)
-    smooth_ms, smooth_bytes = s.bench_sweep(0, 0, 20)
-    achieved = sweep_bytes / (sweep_ms * 1e-3) / 1e9
     own = s.owned_voxels
-    # the ncu capture is of one launch at 512^3 on one GPU: only quote it for that case
-    traffic = ncu_traffic("relax_vec4_jacobi_3d") if (world == 1 and n == 512) else None
+
+    def sweep(kind_id, reps):
+        try:
+            ms_k, by = s.bench_sweep(kind_id, 0, reps)
+        except pkg.FluidSolverError:
+            return None
+        return job.max_over_ranks(ms_k), by
+
+    fl = 1 if obstacle else 0
+    kernel_table = [
+        # (bench kind, name, reference job, compulsory B/voxel of THIS kernel, sweeps of the reference it replaces)
+        (7, "relax_pair_kernel<JACOBI>", "2 x (LinearSolveIterationJob + BoundaryJob)", 12 + fl, 2),
+        (8, "relax_pair_kernel<SMOOTH>", "2 x (DiffuseJob + BoundaryJob)", 8 + fl, 2),
+        (9, "relax_pair_kernel<RED_BLACK>", "red-black full sweep (both colours + set_bnd)", 12 + fl, 1),
+        (1, "relax_vec4<JACOBI>", "LinearSolveIterationJob + BoundaryJob", 12 + fl, 1),
+        (0, "relax_vec4<SMOOTH>", "DiffuseJob + BoundaryJob", 8 + fl, 1),
+        (2, "rb_vec4 x2", "red-black full sweep as two colour launches", 24 + 2 * fl, 1),
+        (3, "advect (scalar)", "AdvectJob + BoundaryJob", 20 + fl, 1),
+        (4, "advect_velocity (3 components fused)", "3 x (AdvectJob + BoundaryJob)", 24 + fl, 3),
+        (5, "divergence_vec4", "ProjectDivergenceJob + 2 BoundaryJob", 16, 1),
+        (6, "gradient_vec4", "ProjectVelocityAdjustJob + 3 BoundaryJob", 28 + fl, 1),
+    ]
+    kernels = []
+    measure = [7, 1, 0] if args.no_kernels else [k[0] for k in kernel_table]
+    if world > 1:
+        measure = [k for k in measure if k in (0, 1, 2, 7, 8, 9)]   # the once-per-step kernels peer-read neighbours' live fields
+    order = [k for k in (3, 4, 5, 7, 8, 9, 1, 0, 2, 6) if k in measure]   # gradient last: it overwrites the velocities
+    results = {}
+    for kid in order:
+        results[kid] = sweep(kid, 5 if kid in (3, 4, 5, 6) else 20)
+    for kid, name, job_name, bpv, nsweeps in kernel_table:
+        r = results.get(kid)
+        if not r:
+            continue
+        ms_k, _ = r
+        gbs = bpv * own / (ms_k * 1e-3) / 1e9
+        kernels.append({"kernel": name, "replaces": job_name, "bytes_per_voxel": bpv, "avg_launch_ms": ms_k,
+                        "achieved_GBps": gbs, "frac": gbs / peak, "reference_sweeps_per_launch": nsweeps})
+    by_name = {k["kernel"]: k for k in kernels}
+    dom = by_name.get("relax_pair_kernel<RED_BLACK>" if kind else "relax_pair_kernel<JACOBI>") or by_name.get("relax_vec4<JACOBI>")
+    traffic_key = {"relax_pair_kernel<JACOBI>": "relax_pair_jacobi_3d", "relax_pair_kernel<RED_BLACK>": "relax_pair_rb_3d",
+                   "relax_vec4<JACOBI>": "relax_vec4_jacobi_3d"}[dom["kernel"]]
+    traffic = ncu_traffic(traffic_key) if (world == 1 and n == 512 and args.scaling == "strong") else None
+    step_bpv = step_bytes_per_voxel(kd, kp)
     roofline = {
-        "bound": "hbm", "kernel": "relax_vec4<JACOBI,3D>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_launch": sweep_bytes, "avg_launch_ms": sweep_ms,
-        "frac_of_8000_nominal": achieved / 8000.0,
-        "smoother_GBps": smooth_bytes / (smooth_ms * 1e-3) / 1e9,
-        "step_level": {"bytes_per_voxel": step_bytes_per_voxel(kd, kp),
-                       "achieved_GBps": step_bytes_per_voxel(kd, kp) * own * world / (ms / args.steps * 1e-3) / 1e9 / world,
-                       "note": "per-GPU, reference-structure algorithmic bytes / measured step time"},
+        "bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
+        "frac": dom["frac"], "traffic": traffic, "peak_source": peak_src,
+        "bytes_per_voxel": dom["bytes_per_voxel"], "algorithmic_bytes_per_launch": dom["bytes_per_voxel"] * own,
+        "avg_launch_ms": dom["avg_launch_ms"], "frac_of_8000_nominal": dom["achieved_GBps"] / 8000.0,
+        "reference_sweeps_per_launch": dom["reference_sweeps_per_launch"],
+        "reference_structure_GBps": dom["achieved_GBps"] * dom["reference_sweeps_per_launch"],
+        "note": "achieved = this kernel's compulsory bytes (in + rhs + flags + out) / its launch time; a fused pair does two "
+                "sweeps of the reference per launch, so against SURVEY.md 8(d)'s per-sweep figure it counts twice "
+                "(reference_structure_GBps)",
+        "kernels": kernels,
+        "step_level": {"bytes_per_voxel": step_bpv,
+                       "achieved_GBps": step_bpv * own / (ms / args.steps * 1e-3) / 1e9,
+                       "frac": step_bpv * own / (ms / args.steps * 1e-3) / 1e9 / peak,
+                       "note": "per-GPU, reference-structure algorithmic bytes (88 K_d + 26 K_p + 182 B/voxel) / measured step time; "
+                               "fused sweeps make this exceed 1"},
     }
+    s.close()
 
     line = {
-        "metric": "Gvoxel-updates/s per full fluid step", "value": value, "unit": "Gvoxel-updates/s",
+        "metric": METRIC, "value": value, "unit": "Gvoxel-updates/s",
         "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": cfg, "grid": [n, n, n], "iters_diffuse": kd, "iters_pressure": kp,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": cfg, "grid": list(dims), "iters_diffuse": kd, "iters_pressure": kp,
                    "solver": "red-black" if kind else "jacobi", "dt": dt, "obstacle": "sphere r=0.1N" if obstacle else "none",
-                   "parallelism": f"z-slabs x{world}", "cuda_graph": not args.no_graph,
+                   "parallelism": f"z-slabs x{world}", "cuda_graph": graph,
                    "l2": "state (45 B/voxel) is larger than L2; no flush needed"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.steps * 1e3,
-                "blocking_readback_value": n ** 3 * args.steps / e2e_blocking_s / 1e9,
+                "frame_value": voxels * args.steps / frame_s / 1e9,
+                "frame_d2h_bytes_per_step": int(rgba.nbytes + 12),
                 "note": "per step: fs_add_source_cells (host->device) + fs_step + fs_get_field_async(density, pressure) into "
-                        "pinned host memory, fs_wait_transfers before the clock stops; blocking_readback_value = same loop with fs_get_field"},
+                        "pinned host memory, fs_wait_transfers before the clock stops; frame_value = sources + fs_step + "
+                        "fs_render_rgba(mid plane) + fs_get_metrics, the drop-in's Update()"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if check is not None:
+        line["parity_check"] = check
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        sample = 128 if n >= 128 else n
-        csteps = 8
-        val, cms = cpu_oracle_rate(sample, kd, kp, csteps, 1)
-        line["cpu_baseline"] = {"value": val, "unit": "Gvoxel-updates/s", "cores": os.cpu_count(), "kind": "port",
-                                "sample": f"{sample}^3 sub-grid, same K_d/K_p, {csteps} steps after 1 warm-up ({cms:.0f} ms/step)"}
+        _, line["cpu_baseline"] = cpu_baseline_block(n, kd, kp, 6, 1)
     else:
         line["cpu_baseline"] = None
-    s.close()
+
+    # ---- side measurements: BASELINE configs[4] (1024^3, K_p = 100) and weak scaling ------------------------------
+    if not args.no_extra and args.workload == "512" and args.scaling == "strong":
+        extra = {}
+        for key, edims, ekind in (("1024_jacobi", (1024, 1024, 1024), 0), ("1024_red_black", (1024, 1024, 1024), 1),
+                                  ("weak_1024x1024x128_per_gpu_red_black", (1024, 1024, 128 * world), 1)):
+            try:
+                extra[key] = short_run(pkg, job, lib, edims, 20, 100, ekind, steps=3, warmup=2, graph=graph)
+                extra[key]["scaling"] = "weak" if key.startswith("weak") else "strong"
+            except Exception as e:  # keep the headline line even if a side run fails (e.g. out of memory)
+                extra[key] = {"error": repr(e)[:300]}
+        line["extra"] = extra
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
