@@ -38,7 +38,9 @@ struct CudaExec {
     bool force_generic = false; // FS_FORCE_GENERIC=1: scalar per-cell kernels for the sweeps (tests)
     int tune_zchunk = 0, tune_by = 0; // FS_ZCHUNK / FS_BLOCK_Y: override the sweep's z chunk length / CTA rows (experiments)
     int pair_rows = FS_PAIR_MAX_ROWS, pair_zchunk = 0; // FS_PAIR_ROWS / FS_PAIR_ZCHUNK (experiments)
-    bool no_pair = false;       // FS_NO_PAIR=1: never use the fused two-stage sweep (tests compare both paths)
+    int pair_mode = 2;          // FS_PAIR: 0 never use the fused two-stage sweep, 1 always, 2 auto (see pair_supported)
+    bool pair_force = false;
+    bool pair_slabs = true;     // FS_PAIR_SLABS=0: auto mode does not fuse Jacobi / smoother sweeps on z-slabs
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
     bool use_graph = false;
@@ -102,7 +104,9 @@ struct CudaExec {
         if (const char *e = getenv("FS_BLOCK_Y")) tune_by = atoi(e);
         if (const char *e = getenv("FS_PAIR_ROWS")) pair_rows = atoi(e);
         if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
-        if (const char *e = getenv("FS_NO_PAIR")) no_pair = e[0] == '1';
+        if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
+        if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
+        if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
         if (pair_rows < 3) pair_rows = 3;
         if (pair_rows > FS_PAIR_MAX_ROWS) pair_rows = FS_PAIR_MAX_ROWS;
         const char *la = getenv("FS_L2_AHEAD");
@@ -112,6 +116,7 @@ struct CudaExec {
     void close() {
         invalidate_graph();
         halo_close();
+        source_close();
         if (d_sum) cudaFree(d_sum);
         if (d_max) cudaFree(d_max);
         if (scratch) cudaFree(scratch);
@@ -282,13 +287,22 @@ struct CudaExec {
     }
     // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
-    bool pair_supported(const FsGrid &g, float c) const {
+    // Policy (FS_PAIR = 0 never / 1 always / unset: auto).  Measured on B200 (profiles/r02b_pair_kernel.md): the fused
+    // kernel moves 13 B/voxel per two stages but is issue bound -- 0.64 ms per Jacobi pair at 512^3 against 2 x 0.26 ms
+    // for two single sweeps that already run at the HBM roofline; the red-black form beats its two-launch version
+    // (0.66 vs 0.75 ms).  So auto = red-black always; Jacobi / smoother pairs only on z-slabs, where halving the number
+    // of launches and halo exchanges is worth more than the issue cost.
+    bool pair_supported(const FsGrid &g, float c, int kind) const {
         const bool c_ok = c != 0.0f && c == c && c - c == 0.0f;
-        return g.hz && g.nx % 4 == 0 && !force_generic && !no_pair && c_ok;
+        if (!(g.hz && g.nx % 4 == 0 && !force_generic && c_ok)) return false;
+        if (pair_force) return true;                     // fs_bench_sweep times the kernel whatever the policy says
+        if (pair_mode == 0) return false;
+        if (pair_mode == 1) return true;
+        return kind == FS_PAIR_RED_BLACK || (halo_on && pair_slabs);
     }
     bool relax_pair(int kind, const FsGrid &g, const float *in, const float *rhs, float *out, const uint8_t *flags,
                     float a, float c, int b, bool in_zero, bool fuse_halo) {
-        if (!pair_supported(g, c)) return false;
+        if (!pair_supported(g, c, kind)) return false;
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return true;
@@ -463,15 +477,44 @@ struct CudaExec {
     void axpy(float *dst, const float *src, long long n) {
         linear(n, [=] __device__(long long t) { dst[t] += src[t]; });
     }
-    void scatter_add(float *dst[4], const long long *idx, const float *src[4], long long n) {
-        const size_t ib = sizeof(long long) * n, fb = sizeof(float) * n;
-        char *s = (char *)get_scratch(ib + 4 * fb);
-        if (!s) return;
-        FS_CUDA(cudaMemcpyAsync(s, idx, ib, cudaMemcpyHostToDevice, st));
-        for (int f = 0; f < 4; f++)
-            if (dst[f]) FS_CUDA(cudaMemcpyAsync(s + ib + f * fb, src[f], fb, cudaMemcpyHostToDevice, st));
-        const long long *di = (const long long *)s;
-        const float *a0 = (const float *)(s + ib), *a1 = a0 + n, *a2 = a1 + n, *a3 = a2 + n;
+    // ---- source staging ring: pinned host slot -> device slot -> scatter kernel, no per-call synchronisation ----
+    struct SourceSlot {
+        char *host = nullptr, *dev = nullptr;
+        size_t bytes = 0;
+        cudaEvent_t done = nullptr;
+        bool pending = false;
+    };
+    static const int kSourceSlots = 4;
+    SourceSlot src_slots[kSourceSlots];
+    int src_next = 0, src_cur = 0;
+    bool source_stage(long long cap, long long **idx, float *amt[4]) {
+        SourceSlot &sl = src_slots[src_cur = src_next];
+        src_next = (src_next + 1) % kSourceSlots;
+        if (sl.pending) { FS_CUDA(cudaEventSynchronize(sl.done)); sl.pending = false; } // only if the GPU is a whole ring behind
+        const size_t need = (sizeof(long long) + 4 * sizeof(float)) * (size_t)cap;
+        if (need > sl.bytes) {
+            if (sl.host) cudaFreeHost(sl.host);
+            if (sl.dev) cudaFree(sl.dev);
+            sl.host = sl.dev = nullptr;
+            sl.bytes = need * 2;
+            if (cudaMallocHost(&sl.host, sl.bytes) != cudaSuccess || cudaMalloc(&sl.dev, sl.bytes) != cudaSuccess) {
+                msg = "source staging allocation failed"; bad = true; sl.bytes = 0;
+                return false;
+            }
+            if (!sl.done) FS_CUDA(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+        }
+        *idx = (long long *)sl.host;
+        float *f = (float *)(sl.host + sizeof(long long) * (size_t)cap);
+        for (int k = 0; k < 4; k++) amt[k] = f + (size_t)cap * k;
+        return true;
+    }
+    void scatter_add_staged(float *dst[4], long long cap, long long n) {
+        if (n <= 0) return;
+        SourceSlot &sl = src_slots[src_cur];
+        const size_t used = (sizeof(long long) + 4 * sizeof(float)) * (size_t)cap;
+        FS_CUDA(cudaMemcpyAsync(sl.dev, sl.host, used, cudaMemcpyHostToDevice, st));
+        const long long *di = (const long long *)sl.dev;
+        const float *a0 = (const float *)(sl.dev + sizeof(long long) * (size_t)cap), *a1 = a0 + cap, *a2 = a1 + cap, *a3 = a2 + cap;
         float *d0 = dst[0], *d1 = dst[1], *d2 = dst[2], *d3 = dst[3];
         // duplicates in idx are legal (two source cells clamped to one voxel): use atomics
         linear(n, [=] __device__(long long t) {
@@ -481,7 +524,103 @@ struct CudaExec {
             if (d2) atomicAdd(d2 + c, a2[t]);
             if (d3) atomicAdd(d3 + c, a3[t]);
         });
-        FS_CUDA(cudaStreamSynchronize(st)); // host arrays are only valid during the call
+        FS_CUDA(cudaEventRecord(sl.done, st));
+        sl.pending = true;
+    }
+    void source_close() {
+        for (SourceSlot &sl : src_slots) {
+            if (sl.host) cudaFreeHost(sl.host);
+            if (sl.dev) cudaFree(sl.dev);
+            if (sl.done) cudaEventDestroy(sl.done);
+            sl = SourceSlot{};
+        }
+    }
+
+    // ---- obstacle bookkeeping on the device ------------------------------------------------------------------------
+    // any_local: some cell of the local planes (ghosts included) is an obstacle; list: local indices of the obstacle cells
+    // on interior rows / columns of local planes [kl0, kl1) (the owned interior planes), in no particular order (the mirror
+    // pass that consumes it is order independent).
+    bool scan_obstacles(const FsGrid &g, const uint8_t *mask, int kl0, int kl1, bool *any_local, long long **list, long long *count) {
+        unsigned long long *ctr = (unsigned long long *)get_scratch(3 * sizeof(unsigned long long));
+        if (!ctr) return false;
+        FS_CUDA(cudaMemsetAsync(ctr, 0, 3 * sizeof(unsigned long long), st));
+        const long long n = g.sz * g.nzl;
+        const int nx = g.nx, ny = g.ny;
+        const long long sz = g.sz;
+        auto interior_owned = [=] __device__(long long t) {
+            const int i = (int)(t % nx), j = (int)((t / nx) % ny), kl = (int)(t / sz);
+            return i >= 1 && i <= nx - 2 && j >= 1 && j <= ny - 2 && kl >= kl0 && kl < kl1;
+        };
+        linear(n, [=] __device__(long long t) {
+            if (!mask[t]) return;
+            atomicAdd(ctr + 0, 1ull); // (rare cells: contention is irrelevant next to the plane-sized reads)
+            if (interior_owned(t)) atomicAdd(ctr + 1, 1ull);
+        });
+        unsigned long long h[3] = {0, 0, 0};
+        FS_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        *any_local = h[0] != 0;
+        *count = (long long)h[1];
+        *list = nullptr;
+        if (h[1] == 0) return !bad;
+        long long *out = (long long *)alloc(sizeof(long long) * h[1]);
+        if (!out) return false;
+        linear(n, [=] __device__(long long t) {
+            if (mask[t] && interior_owned(t)) out[atomicAdd(ctr + 2, 1ull)] = t;
+        });
+        *list = out;
+        return !bad;
+    }
+    // SetupObstacles on the device (next row N4): inside test, the reference's 4-neighbour flood fill on the xy cross
+    // section, the local planes of the mask, and the GLOBAL obstacle counts (evaluated over the whole grid analytically,
+    // so that every slab takes the same decisions without any exchange).
+    bool build_shape(const FsGrid &g, const fs_obstacle_shape &sh, uint8_t *mask, long long *total, long long *interior) {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const bool hz = g.hz != 0;
+        const long long plane = g.sz;
+        uint8_t *inside = (uint8_t *)alloc(2 * plane + 2 * sizeof(unsigned long long) + 16);
+        if (!inside) return false;
+        uint8_t *reach = inside + plane;
+        unsigned long long *ctr = (unsigned long long *)(inside + ((2 * plane + 15) / 16) * 16);
+        FS_CUDA(cudaMemsetAsync(inside, 0, 2 * plane + 2 * sizeof(unsigned long long) + 16, st));
+        const bool need_fill = !(sh.kind == 0 && hz);
+        const bool seed_in_grid = sh.seed_x >= 0 && sh.seed_x < nx && sh.seed_y >= 0 && sh.seed_y < ny && (!hz || (sh.seed_z >= 0 && sh.seed_z < nz));
+        bool seed_ok = false;
+        const fs_obstacle_shape shape = sh;
+        if (need_fill) {
+            linear(plane, [=] __device__(long long t) {
+                const int x = (int)(t % nx), y = (int)(t / nx);
+                inside[t] = shape.kind == 0 ? fs_shape_inside_circle(shape, false, x, y, 0) : fs_shape_inside_xy(shape, x, y);
+            });
+            if (seed_in_grid) {
+                flood_fill_kernel<<<1, 1024, 0, st>>>(nx, ny, inside, reach, shape.seed_x, shape.seed_y);
+                launches++;
+            }
+            seed_ok = seed_in_grid && fs_shape_in_span(sh, hz && sh.kind != 0, sh.seed_z);
+        } else {
+            seed_ok = seed_in_grid && fs_shape_inside_circle(sh, true, sh.seed_x, sh.seed_y, sh.seed_z);
+        }
+        const int zoff = g.zoff;
+        const long long nloc = plane * g.nzl;
+        const bool ok = seed_ok;
+        linear(nloc, [=] __device__(long long t) {
+            const int x = (int)(t % nx), y = (int)((t / nx) % ny), kl = (int)(t / plane);
+            mask[t] = ok ? fs_shape_mask(shape, hz, nx, reach, ok, x, y, kl + zoff) : 0;
+        });
+        const long long ncell = plane * nz;
+        linear(ncell, [=] __device__(long long t) {
+            const int x = (int)(t % nx), y = (int)((t / nx) % ny), z = (int)(t / plane);
+            if (!ok || !fs_shape_mask(shape, hz, nx, reach, ok, x, y, z)) return;
+            atomicAdd(ctr + 0, 1ull);
+            if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && (!hz || (z >= 1 && z <= nz - 2))) atomicAdd(ctr + 1, 1ull);
+        });
+        unsigned long long h[2] = {0, 0};
+        FS_CUDA(cudaMemcpyAsync(h, ctr, sizeof(h), cudaMemcpyDeviceToHost, st));
+        FS_CUDA(cudaStreamSynchronize(st));
+        cudaFree(inside);
+        *total = (long long)h[0];
+        *interior = (long long)h[1];
+        return !bad;
     }
     void metrics(const FsGrid &g, const float *d, const float *ux, const float *uy, const float *uz, double *sum, float *mx) {
         FS_CUDA(cudaMemsetAsync(d_sum, 0, sizeof(double), st));

@@ -59,6 +59,22 @@ int fs_slab_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end, int64_t 
 
 int fs_set_obstacles(fs_solver *s, const uint8_t *mask, int64_t n) { FS_GUARD(s); return c.set_obstacles(mask, n); }
 
+int fs_slab_halo_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end) {
+    if (!s) return FS_ERR_BAD_ARGUMENT;
+    if (z_begin) *z_begin = s->core.g.zoff;
+    if (z_end) *z_end = s->core.g.zoff + s->core.g.nzl;
+    return FS_OK;
+}
+
+int fs_set_obstacles_slab(fs_solver *s, const uint8_t *mask, int64_t n, int32_t global_any, int32_t global_interior) {
+    FS_GUARD(s);
+    return c.set_obstacles_slab(mask, n, global_any != 0, global_interior != 0);
+}
+
+int fs_build_obstacles(fs_solver *s, const fs_obstacle_shape *shape, int64_t *obstacle_cells) { FS_GUARD(s); return c.build_obstacles(shape, obstacle_cells); }
+
+int fs_get_obstacles(fs_solver *s, uint8_t *out, int64_t n) { FS_GUARD(s); return c.get_obstacles(out, n); }
+
 int fs_add_density(fs_solver *s, float x, float y, float z, float amount) {
     FS_GUARD(s);
     return c.add_cells(1, &x, &y, &z, &amount, nullptr, nullptr, nullptr);
@@ -259,11 +275,13 @@ int fs_bench_sweep(fs_solver *s, int32_t kind_and_fill, int32_t b, int32_t reps,
         case 9: ok = c.ex.relax_pair(FS_PAIR_RED_BLACK, c.g, c.vx0, c.vy0, c.tmp, c.fl(), a, cc, b, false, true); break;
         }
     };
+    c.ex.pair_force = true;
     for (int w = 0; w < 2; w++) once(); // warm-up
-    if (!ok) return c.fail(FS_ERR_UNSUPPORTED, "the fused pair kernel does not support this grid");
+    if (!ok) { c.ex.pair_force = false; return c.fail(FS_ERR_UNSUPPORTED, "the fused pair kernel does not support this grid"); }
     c.ex.timer_start();
     for (int r = 0; r < reps; r++) once();
     const float ms = c.ex.timer_stop();
+    c.ex.pair_force = false;
     if (avg_ms) *avg_ms = ms / (float)reps;
     if (algo_bytes) *algo_bytes = per_voxel * (double)interior;
     return c.check();

@@ -359,6 +359,42 @@ FS_HD uint8_t fs_flags_cell(const FsGrid &g, const uint8_t *mask, int i, int j, 
     return f;
 }
 
+// ---- obstacle shapes (next row N4) --------------------------------------------------------------------------------
+// IsInsideShape, FluidSim.cs:353-388, for cell (x, y[, z]).  The 2D expressions are the reference's, term by term;
+// in 3D a Circle becomes a sphere (z term appended last) and Rectangle / Airfoil are extruded over
+// center_z +- depth/2 (strict, like the reference's x / y tests).
+FS_HD bool fs_shape_inside_xy(const fs_obstacle_shape &sh, int x, int y) { // Rectangle / Airfoil cross-section
+    const float centerX = sh.center_x, centerY = sh.center_y;
+    if (sh.kind == 1) {
+        const float halfWidth = sh.width * 0.5f, halfHeight = sh.height * 0.5f;
+        return x > (centerX - halfWidth) && x < (centerX + halfWidth) && y > (centerY - halfHeight) && y < (centerY + halfHeight);
+    }
+    const float chord = 2 * sh.width;
+    const float thickness = 0.15f;
+    const float normX = (x - centerX + chord / 2) / chord;
+    const float normY = (y - centerY) / chord;
+    if (normX < 0 || normX > 1 || fabsf(normY) > thickness) return false;
+    const float halfThickness = 5 * thickness * (0.2969f * sqrtf(normX) - 0.1260f * normX - 0.3516f * normX * normX +
+                                                 0.2843f * normX * normX * normX - 0.1015f * normX * normX * normX * normX);
+    return fabsf(normY) <= halfThickness;
+}
+FS_HD bool fs_shape_inside_circle(const fs_obstacle_shape &sh, bool hz, int x, int y, int z) {
+    float d2 = (x - sh.center_x) * (x - sh.center_x) + (y - sh.center_y) * (y - sh.center_y);
+    if (hz) d2 = d2 + (z - sh.center_z) * (z - sh.center_z);
+    return d2 < sh.radius * sh.radius;
+}
+FS_HD bool fs_shape_in_span(const fs_obstacle_shape &sh, bool hz, int z) {
+    if (!hz) return true;
+    const float halfDepth = sh.depth * 0.5f;
+    return z > (sh.center_z - halfDepth) && z < (sh.center_z + halfDepth);
+}
+// Final mask value of cell (x, y, z) given the flood-filled cross-section `reach` (nx*ny bytes; Rectangle / Airfoil, and
+// the 2D Circle) -- or, for the 3D sphere, the inside test itself gated by "the seed cell is inside".
+FS_HD uint8_t fs_shape_mask(const fs_obstacle_shape &sh, bool hz, int nx, const uint8_t *reach, bool seed_ok, int x, int y, int z) {
+    if (sh.kind == 0 && hz) return (seed_ok && fs_shape_inside_circle(sh, true, x, y, z)) ? 1 : 0;
+    return (reach[x + (long long)y * nx] && fs_shape_in_span(sh, hz && sh.kind != 0, z)) ? 1 : 0;
+}
+
 // ---- visualisation colour mapping (next row N2) ------------------------------------------------------------------
 // UpdateVisualizationJob.Execute, FluidSim.cs:1888-1979, for one cell of one xy plane.  Color.Lerp clamps t to
 // [0,1]; Color.black = (0,0,0,1); the "very high pressure" colour is (1, 0.5, 0, 1) (:1962).

@@ -107,42 +107,54 @@ struct SolverCore {
     const uint8_t *fl() const { return any_obstacle ? flags : nullptr; }
 
     // ---- obstacles (SetupObstacles output, FluidSim.cs:302-327) --------------------------------
-    int set_obstacles(const uint8_t *gmask, long long n) {
-        if (!gmask || n != g.sz * g.nz) return fail(FS_ERR_BAD_ARGUMENT, "mask must have nx*ny*nz bytes");
-        const uint8_t *loc = gmask + g.sz * g.zoff;
-        ex.upload(mask, loc, nloc);
+    // The mask of the local planes is on the device: derive the flag bytes, the local "any obstacle" bit and the list of
+    // owned interior obstacle cells there too (no host pass over the grid), and record the GLOBAL presence bits.
+    int finish_obstacles(bool global_any, bool global_interior) {
         ex.build_flags(g, mask, flags);
-        std::vector<long long> list;
-        bool any = false;
-        for (long long i = 0; i < nloc && !any; i++) any = loc[i] != 0;
-        const int k0 = g.hz ? std::max(zb, 1) : 0, k1 = g.hz ? std::min(ze, g.nz - 1) : 1;
-        if (any)
-            for (int k = k0; k < k1; k++)
-                for (int j = 1; j <= g.ny - 2; j++)
-                    for (int i = 1; i <= g.nx - 2; i++)
-                        if (gmask[i + j * g.sy + k * g.sz]) list.push_back(fs_idx(g, i, j, k - g.zoff));
-        g_any_obstacle = g_interior_obstacle = false;
-        {
-            const long long total = g.sz * g.nz;
-            for (long long i = 0; i < total && !g_any_obstacle; i++) g_any_obstacle = gmask[i] != 0;
-            const int gk0 = g.hz ? 1 : 0, gk1 = g.hz ? g.nz - 1 : 1;
-            for (int k = gk0; k < gk1 && g_any_obstacle && !g_interior_obstacle; k++)
-                for (int j = 1; j <= g.ny - 2 && !g_interior_obstacle; j++) {
-                    const uint8_t *row = gmask + j * g.sy + k * g.sz;
-                    for (int i = 1; i <= g.nx - 2; i++)
-                        if (row[i]) { g_interior_obstacle = true; break; }
-                }
-        }
         ex.free(obst_list);
         obst_list = nullptr;
-        n_obst = (long long)list.size();
+        n_obst = 0;
+        const int k0 = (g.hz ? std::max(zb, 1) : 0) - g.zoff, k1 = (g.hz ? std::min(ze, g.nz - 1) : 1) - g.zoff;
+        bool any = false;
+        if (!ex.scan_obstacles(g, mask, k0, k1, &any, &obst_list, &n_obst)) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
         any_obstacle = any;
-        if (n_obst) {
-            obst_list = (long long *)ex.alloc(sizeof(long long) * n_obst);
-            if (!obst_list) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
-            ex.upload(obst_list, list.data(), sizeof(long long) * n_obst);
-        }
+        g_any_obstacle = global_any;
+        g_interior_obstacle = global_interior;
         ex.invalidate_graph();
+        return check();
+    }
+    int set_obstacles(const uint8_t *gmask, long long n) {
+        if (!gmask || n != g.sz * g.nz) return fail(FS_ERR_BAD_ARGUMENT, "mask must have nx*ny*nz bytes");
+        ex.upload(mask, gmask + g.sz * g.zoff, nloc);
+        // global presence: one early-exit pass on the host (the typical mask has an obstacle and stops at once)
+        bool ga = false, gi = false;
+        const long long total = g.sz * g.nz;
+        for (long long i = 0; i < total && !ga; i++) ga = gmask[i] != 0;
+        const int gk0 = g.hz ? 1 : 0, gk1 = g.hz ? g.nz - 1 : 1;
+        for (int k = gk0; k < gk1 && ga && !gi; k++)
+            for (int j = 1; j <= g.ny - 2 && !gi; j++) {
+                const uint8_t *row = gmask + j * g.sy + k * g.sz;
+                for (int i = 1; i <= g.nx - 2; i++)
+                    if (row[i]) { gi = true; break; }
+            }
+        return finish_obstacles(ga, gi);
+    }
+    int set_obstacles_slab(const uint8_t *lmask, long long n, bool global_any, bool global_interior) {
+        if (!lmask || n != nloc) return fail(FS_ERR_BAD_ARGUMENT, "mask must hold the planes of fs_slab_halo_range");
+        ex.upload(mask, lmask, nloc);
+        return finish_obstacles(global_any, global_interior);
+    }
+    // Device-side SetupObstacles (next row N4): every handle builds its own planes from the shape parameters.
+    int build_obstacles(const fs_obstacle_shape *sh, int64_t *cells) {
+        if (!sh || sh->kind < 0 || sh->kind > 2) return fail(FS_ERR_BAD_ARGUMENT, "unknown obstacle shape");
+        long long total = 0, interior = 0;
+        if (!ex.build_shape(g, *sh, mask, &total, &interior)) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
+        if (cells) *cells = total;
+        return finish_obstacles(total > 0, interior > 0);
+    }
+    int get_obstacles(uint8_t *out, long long n) {
+        if (!out || n != nowned) return fail(FS_ERR_BAD_ARGUMENT, "n must equal the owned voxel count");
+        ex.download(out, mask + g.sz * g.kb, (size_t)nowned);
         return check();
     }
 
@@ -155,24 +167,28 @@ struct SolverCore {
         if (k < g.zoff || k >= g.zoff + g.nzl) return -1;
         return fs_idx(g, i, j, k - g.zoff);
     }
+    // The cell list goes through a small ring of host staging buffers (pinned on the GPU build): the call returns as
+    // soon as the copy and the scatter kernel are enqueued -- no stream synchronisation per frame.
     int add_cells(long long count, const float *x, const float *y, const float *z, const float *d, const float *ax,
                   const float *ay, const float *az) {
         if (count < 0 || !x || !y) return fail(FS_ERR_BAD_ARGUMENT, "bad source list");
-        std::vector<long long> idx;
-        std::vector<float> amt[4];
+        if (count == 0) return FS_OK;
+        long long *idx = nullptr;
+        float *amt[4] = {};
+        if (!ex.source_stage(count, &idx, amt)) return fail(FS_ERR_OUT_OF_MEMORY, ex.error());
+        long long m = 0;
         for (long long n = 0; n < count; n++) {
             const long long c = source_cell(x[n], y[n], z ? z[n] : 0.0f);
             if (c < 0) continue;
-            idx.push_back(c);
-            amt[0].push_back(d ? d[n] : 0.0f);
-            amt[1].push_back(ax ? ax[n] : 0.0f);
-            amt[2].push_back(ay ? ay[n] : 0.0f);
-            amt[3].push_back(az ? az[n] : 0.0f);
+            idx[m] = c;
+            amt[0][m] = d ? d[n] : 0.0f;
+            amt[1][m] = ax ? ax[n] : 0.0f;
+            amt[2][m] = ay ? ay[n] : 0.0f;
+            amt[3][m] = az ? az[n] : 0.0f;
+            m++;
         }
-        if (idx.empty()) return FS_OK;
         float *dst[4] = {d ? density : nullptr, ax ? vx : nullptr, ay ? vy : nullptr, (az && g.hz) ? vz : nullptr};
-        const float *src[4] = {amt[0].data(), amt[1].data(), amt[2].data(), amt[3].data()};
-        ex.scatter_add(dst, idx.data(), src, (long long)idx.size());
+        ex.scatter_add_staged(dst, count, m);
         return check();
     }
     int add_dense(const float *d, const float *ax, const float *ay, const float *az) {
@@ -212,13 +228,13 @@ struct SolverCore {
     }
     // Whether sweeps of field kind b may be fused in pairs: no obstacle mirroring between the two stages.
     bool needs_mirror(int b) const { return b != 0 && g_interior_obstacle && (b != 3 || g.hz); }
-    bool pair_ok(int b, float c) const { return !needs_mirror(b) && ex.pair_supported(g, c); }
+    bool pair_ok(int b, float c, int kind) const { return !needs_mirror(b) && ex.pair_supported(g, c, kind); }
     // pass 1, DiffuseWithJobs :1292-1357.  Result ends in `x` (roles of x and tmp may swap).
     void smooth(int b, float *&x, const float *x0, float a, float c, int iters) {
         if (iters == 0) { ex.copy(x, x0, sizeof(float) * nloc); return; }
         float *A = tmp, *B = x;
         const float *in = x0;
-        const bool pairs = pair_ok(b, c);
+        const bool pairs = pair_ok(b, c, FS_PAIR_SMOOTH);
         // Obstacle cells keep the stale content of the write buffer (DiffuseJob does not write them, :1055).  Both
         // reference buffers start as copies of x0 (:1299-1300) and, without mirroring, nothing ever changes those cells:
         // they hold x0 throughout, so `stale = x0` is exact for every iteration.  With mirroring (b != 0 and interior
@@ -244,7 +260,7 @@ struct SolverCore {
     void lin_solve(int b, float *&x, const float *rhs, float a, float c, int iters, bool zero_guess) {
         if (iters == 0) { if (zero_guess) ex.zero(x, sizeof(float) * nloc); return; }
         float *rd = x, *wr = tmp;
-        const bool pairs = pair_ok(b, c);
+        const bool pairs = pair_ok(b, c, FS_PAIR_JACOBI);
         for (int it = 0; it < iters;) {
             const bool iz = zero_guess && it == 0;
             if (pairs && it + 2 <= iters && ex.relax_pair(FS_PAIR_JACOBI, g, rd, rhs, wr, fl(), a, c, b, iz, true)) {
@@ -261,7 +277,7 @@ struct SolverCore {
     // Red-black Gauss-Seidel (BASELINE config 5).  Fused form: both colour passes and set_bnd in one out-of-place pass
     // (ping-pong like Jacobi).  Fallback: in place, one launch per colour.
     void lin_solve_rb(int b, float *&x, const float *rhs, float a, float c, int iters, bool zero_guess) {
-        if (pair_ok(b, c) && iters > 0) {
+        if (pair_ok(b, c, FS_PAIR_RED_BLACK) && iters > 0) {
             float *rd = x, *wr = tmp;
             for (int it = 0; it < iters; it++) {
                 ex.relax_pair(FS_PAIR_RED_BLACK, g, rd, rhs, wr, fl(), a, c, b, zero_guess && it == 0, true);
@@ -300,7 +316,7 @@ struct SolverCore {
         ex.divergence(g, div, ux, uy, uz);
         // slabs + fused sweeps: the first stage is evaluated one plane into the ghost zone and reads the right-hand
         // side there (a single sweep only reads div on owned planes)
-        if (pair_ok(0, 6.0f)) ex.halo(g, div);
+        if (pair_ok(0, 6.0f, prm.solver_kind == FS_RED_BLACK ? FS_PAIR_RED_BLACK : FS_PAIR_JACOBI)) ex.halo(g, div);
         if (prm.solver_kind == FS_RED_BLACK)
             lin_solve_rb(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true);
         else

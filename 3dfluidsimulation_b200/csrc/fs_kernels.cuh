@@ -416,9 +416,10 @@ __device__ __forceinline__ void fs_vec4_store_ring(float *out, const FsGrid &g, 
 // tile plus a one-cell ring -- (W + 2) float4 columns (only one lane of each outer column is needed, the other three are
 // free SIMD width) x rows -- by a FLATTENED thread index t -> (row = t / (W+2), column = t % (W+2)), so that no lane idles
 // whatever nx is; the same thread then owns the same column in stage 2 (threads of the outer ring idle there).  Per
-// z step: stage 1 at plane k (z-1/z/z+1 of `in` in registers, x/y neighbours through L1 as in relax_vec4), the
-// result goes to shared memory (triple buffered: one barrier per step) and stays in registers as the z column of
-// y1; stage 2 at plane k-1 takes y1's z neighbours from registers and its x/y neighbours from shared memory.
+// z step: the global loads of stage 1 at plane k are issued (z-1/z/z+1 of `in` in registers, x/y neighbours through
+// L1 as in relax_vec4); while they are in flight stage 2 runs at plane k-2 (y1's z neighbours from registers, its
+// x/y neighbours from shared memory); then the stage-1 arithmetic, whose result goes to shared memory (three
+// rotating slots: one barrier per step) and stays in registers as the z column of y1.
 // Ring cells of the intermediate field: Jacobi / smoother stages end with set_bnd, so stage 2 must see
 // y1(ring) = +-y1(nearest interior cell): x faces are fixed up inside the float4 before it is stored, y / z faces
 // are substituted on the fly for the rows / planes next to them (edges and corners are never read by a stencil);
@@ -432,9 +433,9 @@ __device__ __forceinline__ void fs_vec4_store_ring(float *out, const FsGrid &g, 
 template <int KIND>
 __global__ void __launch_bounds__(FS_PAIR_MAX_THREADS, 1)
 relax_pair_kernel(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, float *out,
-           const uint8_t *__restrict__ flags, const float a, const float c, const int b, const int in_zero,
-           const int kl_begin, const int kl_end, const int zchunk, const int zc_base, const int zc_stride,
-           const int l2_ahead, const int wcols, const int rows) {
+                  const uint8_t *__restrict__ flags, const float a, const float c, const int b, const int in_zero,
+                  const int kl_begin, const int kl_end, const int zchunk, const int zc_base, const int zc_stride,
+                  const int l2_ahead, const int wcols, const int rows) {
     __shared__ float4 s_y1[3][FS_PAIR_MAX_THREADS];
     const int cols = wcols + 2;
     const int t = threadIdx.x;
@@ -454,121 +455,125 @@ relax_pair_kernel(const FsGrid g, const float *__restrict__ in, const float *__r
     const long long sy = g.sy, sz = g.sz;
     const FsDivisor dv = fs_make_divisor(c);
     const float sgn_x = b == 1 ? -1.0f : 1.0f, sgn_y = b == 2 ? -1.0f : 1.0f, sgn_z = b == 3 ? -1.0f : 1.0f;
+    const bool yface = j == 1 || j == g.ny - 2;
 
     // running pointers at plane kl = k_lo - 1 (the first stage-1 plane)
     const long long idx0 = live ? fs_idx(g, x0, j, k_lo - 1) : 0;
     const float *pin = in + idx0;
     const float *prh = rhs ? rhs + idx0 : nullptr;
     const uint8_t *pfl = flags ? flags + idx0 : nullptr;
-    float *pout = out + idx0 - sz;                       // stage 2 trails one plane behind
+    float *pout = out + idx0 - 2 * sz;                   // stage 2 trails two planes behind stage 1
 
-    float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 a_prev = zero4, a_cur = zero4, a_next = zero4;    // z column of `in`
-    float4 y_prev = zero4, y_cur = zero4;                    // z column of y1 (planes kl-2, kl-1)
-    float4 r_prev = zero4;                                   // rhs / flags of plane kl-1 for stage 2
-    uint32_t f_prev = 0u;
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a_prev = zero4, a_cur = zero4, a_next = zero4;    // z column of `in`: planes kl-1, kl, kl+1
+    float4 y_a = zero4, y_b = zero4, y_c = zero4;            // z column of y1: planes kl-3, kl-2, kl-1
+    float4 r_p = zero4, r_pp = zero4;                        // rhs of planes kl-1, kl-2 (stage 2 uses kl-2)
+    uint32_t f_p = 0u, f_pp = 0u;
     if (live && !in_zero) {
         a_cur = ld4(pin);
         // plane k_lo - 2 exists unless plane k_lo - 1 is the global ring plane (then stage 1 only passes it through)
         if ((k_lo - 1) + g.zoff >= 1) a_prev = ld4(pin - sz);
     }
 
-    int buf = 0;
-    for (int kl = k_lo - 1; kl <= k_hi; kl++, pin += sz, prh += sz, pfl += sz, pout += sz) {
+    // shared-memory slots of y1 planes kl (written), kl-1, kl-2 (read by stage 2); rotated instead of indexed
+    float4 *s_w = &s_y1[0][t], *s_m = &s_y1[1][t], *s_r = &s_y1[2][t];
+    // Per step kl: (1) issue the global loads of stage 1 at plane kl; (2) stage 2 at plane kl-2 from registers and
+    // shared memory while those loads are in flight; (3) stage 1 arithmetic at plane kl; (4) publish y1(kl), one barrier.
+    for (int kl = k_lo - 1; kl <= k_hi + 1; kl++, pin += sz, prh += sz, pfl += sz, pout += sz) {
         const int k = kl + g.zoff;                       // global plane of stage 1
-        const bool plane_in = k >= 1 && k <= g.nz - 2;   // interior plane: stage 1 updates; ring plane: passes through
-        float4 v1 = a_cur, r4 = zero4;
+        const bool s1 = kl <= k_hi;                      // (the last step only drains stage 2)
+        const bool plane_in = s1 && k >= 1 && k <= g.nz - 2; // interior plane: stage 1 updates; ring plane: passes through
+        const bool upd = live && plane_in && row_in;
+        // ---------------- (1) loads of stage 1 at plane kl ----------------
+        float4 up = zero4, dn = zero4, r4 = zero4;
+        float left = 0.f, right = 0.f;
         uint32_t fl = 0u;
-        // ---------------- stage 1 at plane kl ----------------
-        if (live) {
-            // z column of `in`: plane kl + 1 is needed by this stage (interior plane) or by the next step's
-            if (!in_zero && (plane_in || kl < k_hi)) a_next = ld4(pin + sz);
-            if (plane_in) {
-                if (row_in) {
-                    float4 up = zero4, dn = zero4;
-                    float left = 0.f, right = 0.f;
-                    if (!in_zero) {
-                        up = ld4(pin + sy);
-                        dn = ld4(pin - sy);
-                        if (!first_x) left = __ldg(pin - 1);
-                        if (!last_x) right = __ldg(pin + 4);
-                    }
-                    if (l2_ahead > 0 && kl + l2_ahead <= k_hi) {
-                        if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
-                        if (KIND != FS_PAIR_SMOOTH) prefetch_l2(prh + (long long)l2_ahead * sz);
-                        if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
-                    }
-                    r4 = KIND == FS_PAIR_SMOOTH ? a_cur : ld4_stream(prh);
-                    fl = flags ? ld_flags4(pfl) : 0u;
-                    const float cv[6] = {left, a_cur.x, a_cur.y, a_cur.z, a_cur.w, right};
-                    const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
-                    const float nxv[4] = {a_next.x, a_next.y, a_next.z, a_next.w};
-                    const float pvv[4] = {a_prev.x, a_prev.y, a_prev.z, a_prev.w};
-                    const float rv[4] = {r4.x, r4.y, r4.z, r4.w};
-                    const int par = (j + k) & 1;         // x0 % 4 == 0: lane l has colour (l + j + k) & 1
-                    float v[4];
-#pragma unroll
-                    for (int l = 0; l < 4; l++) {
-                        float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
-                        s = (s + nxv[l]) + pvv[l];
-                        const float val = fs_div(rv[l] + a * s, dv);
-                        bool keep = ((fl >> (8 * l)) & 1u) != 0u || (l == 0 && first_x) || (l == 3 && last_x);
-                        if (KIND == FS_PAIR_RED_BLACK) keep = keep || (((l + par) & 1) != 0);
-                        v[l] = keep ? cv[l + 1] : val;
-                    }
-                    if (KIND != FS_PAIR_RED_BLACK) {     // set_bnd x faces of the intermediate field
-                        if (first_x) v[0] = sgn_x * v[1];
-                        if (last_x) v[3] = sgn_x * v[2];
-                    }
-                    v1 = make_float4(v[0], v[1], v[2], v[3]);
-                }
+        if (live && s1 && !in_zero && (plane_in || kl < k_hi)) a_next = ld4(pin + sz);
+        if (upd) {
+            if (!in_zero) {
+                up = ld4(pin + sy);
+                dn = ld4(pin - sy);
+                if (!first_x) left = __ldg(pin - 1);
+                if (!last_x) right = __ldg(pin + 4);
+            }
+            if (KIND != FS_PAIR_SMOOTH) r4 = ld4_stream(prh);
+            fl = flags ? ld_flags4(pfl) : 0u;
+            if (l2_ahead > 0 && kl + l2_ahead <= k_hi) {
+                if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
+                if (KIND != FS_PAIR_SMOOTH) prefetch_l2(prh + (long long)l2_ahead * sz);
+                if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
             }
         }
-        s_y1[buf][t] = v1;
-        __syncthreads();
-        // ---------------- stage 2 at plane kl - 1 ----------------
-        if (inner && kl - 1 >= k_lo && kl - 1 < k_hi) {
-            const int bp = buf == 0 ? 2 : buf - 1;       // y1 of plane kl - 1
-            const int k2 = k - 1;
-            float4 up = s_y1[bp][t + cols], dn = s_y1[bp][t - cols];
-            float left = s_y1[bp][t - 1].w, right = s_y1[bp][t + 1].x;
-            float4 zp = y_prev, zn = v1;
+        // ---------------- (2) stage 2 at plane kl - 2 ----------------
+        if (inner && kl - 2 >= k_lo && kl - 2 < k_hi) {
+            const int k2 = k - 2;
+            float4 up2 = s_r[cols], dn2 = s_r[-cols];
+            const float left2 = s_r[-1].w, right2 = s_r[1].x;
+            float4 zp = y_a, zn = y_c;
             if (KIND != FS_PAIR_RED_BLACK) {             // set_bnd y / z faces of the intermediate field, on the fly
-                if (j == 1) dn = make_float4(sgn_y * y_cur.x, sgn_y * y_cur.y, sgn_y * y_cur.z, sgn_y * y_cur.w);
-                if (j == g.ny - 2) up = make_float4(sgn_y * y_cur.x, sgn_y * y_cur.y, sgn_y * y_cur.z, sgn_y * y_cur.w);
-                if (k2 == 1) zp = make_float4(sgn_z * y_cur.x, sgn_z * y_cur.y, sgn_z * y_cur.z, sgn_z * y_cur.w);
-                if (k2 == g.nz - 2) zn = make_float4(sgn_z * y_cur.x, sgn_z * y_cur.y, sgn_z * y_cur.z, sgn_z * y_cur.w);
+                if (j == 1) dn2 = make_float4(sgn_y * y_b.x, sgn_y * y_b.y, sgn_y * y_b.z, sgn_y * y_b.w);
+                if (j == g.ny - 2) up2 = make_float4(sgn_y * y_b.x, sgn_y * y_b.y, sgn_y * y_b.z, sgn_y * y_b.w);
+                if (k2 == 1) zp = make_float4(sgn_z * y_b.x, sgn_z * y_b.y, sgn_z * y_b.z, sgn_z * y_b.w);
+                if (k2 == g.nz - 2) zn = make_float4(sgn_z * y_b.x, sgn_z * y_b.y, sgn_z * y_b.z, sgn_z * y_b.w);
             }
-            const float4 rr = KIND == FS_PAIR_SMOOTH ? y_cur : r_prev;
-            const float cv[6] = {left, y_cur.x, y_cur.y, y_cur.z, y_cur.w, right};
-            const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+            const float4 rr = KIND == FS_PAIR_SMOOTH ? y_b : r_pp;
+            const float cv[6] = {left2, y_b.x, y_b.y, y_b.z, y_b.w, right2};
+            const float upv[4] = {up2.x, up2.y, up2.z, up2.w}, dnv[4] = {dn2.x, dn2.y, dn2.z, dn2.w};
             const float nxv[4] = {zn.x, zn.y, zn.z, zn.w}, pvv[4] = {zp.x, zp.y, zp.z, zp.w};
             const float rv[4] = {rr.x, rr.y, rr.z, rr.w};
-            const int par = (j + k2) & 1;
+            const int par = (j + k2) & 1;                // x0 % 4 == 0: lane l has colour (l + j + k) & 1
             float v[4];
 #pragma unroll
             for (int l = 0; l < 4; l++) {
                 float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
                 s = (s + nxv[l]) + pvv[l];
                 const float val = fs_div(rv[l] + a * s, dv);
-                bool keep = ((f_prev >> (8 * l)) & 1u) != 0u || (l == 0 && first_x) || (l == 3 && last_x);
+                bool keep = ((f_pp >> (8 * l)) & 1u) != 0u || (l == 0 && first_x) || (l == 3 && last_x);
                 if (KIND == FS_PAIR_RED_BLACK) keep = keep || (((l + par) & 1) == 0);
                 v[l] = keep ? cv[l + 1] : val;
             }
-            const bool yface = j == 1 || j == g.ny - 2, zface = k2 == 1 || k2 == g.nz - 2;
-            if (!yface && !zface) {
+            if (!yface && k2 != 1 && k2 != g.nz - 2) {
                 if (first_x) v[0] = sgn_x * v[1];
                 if (last_x) v[3] = sgn_x * v[2];
                 st4(pout, v);
             } else {
-                const FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl - 1);
+                const FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl - 2);
                 fs_vec4_store_ring(out, g, pos, v, b);
             }
         }
+        // ---------------- (3) stage 1 arithmetic at plane kl ----------------
+        float4 v1 = a_cur;                               // ring rows / planes / dead lanes pass `in` through
+        if (upd) {
+            const float4 rs = KIND == FS_PAIR_SMOOTH ? a_cur : r4;
+            const float cv[6] = {left, a_cur.x, a_cur.y, a_cur.z, a_cur.w, right};
+            const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};
+            const float nxv[4] = {a_next.x, a_next.y, a_next.z, a_next.w};
+            const float pvv[4] = {a_prev.x, a_prev.y, a_prev.z, a_prev.w};
+            const float rv[4] = {rs.x, rs.y, rs.z, rs.w};
+            const int par = (j + k) & 1;
+            float v[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++) {
+                float s = ((cv[l + 2] + cv[l]) + upv[l]) + dnv[l];
+                s = (s + nxv[l]) + pvv[l];
+                const float val = fs_div(rv[l] + a * s, dv);
+                bool keep = ((fl >> (8 * l)) & 1u) != 0u || (l == 0 && first_x) || (l == 3 && last_x);
+                if (KIND == FS_PAIR_RED_BLACK) keep = keep || (((l + par) & 1) != 0);
+                v[l] = keep ? cv[l + 1] : val;
+            }
+            if (KIND != FS_PAIR_RED_BLACK) {             // set_bnd x faces of the intermediate field
+                if (first_x) v[0] = sgn_x * v[1];
+                if (last_x) v[3] = sgn_x * v[2];
+            }
+            v1 = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        // ---------------- (4) publish y1(kl) ----------------
+        *s_w = v1;
+        __syncthreads();
         a_prev = a_cur; a_cur = a_next;
-        y_prev = y_cur; y_cur = v1;
-        r_prev = r4; f_prev = fl;
-        buf = buf == 2 ? 0 : buf + 1;
+        y_a = y_b; y_b = y_c; y_c = v1;
+        r_pp = r_p; r_p = r4; f_pp = f_p; f_p = fl;
+        float4 *tmp_s = s_r; s_r = s_m; s_m = s_w; s_w = tmp_s;
     }
 }
 
@@ -686,6 +691,34 @@ rb_vec4(const FsGrid g, float *x, const float *__restrict__ rhs, const uint8_t *
         fs_vec4_store_ring(x, g, pos, v, b);
     } else {
         st4(x + idx, v);
+    }
+}
+
+// ---- RecursiveFloodFill, FluidSim.cs:329-351, as a fixed point: a cell of the shape becomes an obstacle once one of
+// its 4 neighbours is one, starting from the seed.  One CTA; `reach` only ever goes 0 -> 1, so the concurrent
+// reads are benign and the fixed point is the reference's fill.  The cross-section is at most 1024^2 cells.
+__global__ void __launch_bounds__(1024)
+flood_fill_kernel(const int nx, const int ny, const uint8_t *__restrict__ inside, uint8_t *reach, const int seed_x, const int seed_y) {
+    __shared__ int changed;
+    volatile uint8_t *r = reach;
+    const long long n = (long long)nx * ny;
+    if (threadIdx.x == 0 && inside[seed_x + (long long)seed_y * nx]) r[seed_x + (long long)seed_y * nx] = 1;
+    while (true) {
+        __syncthreads();
+        if (threadIdx.x == 0) changed = 0;
+        __syncthreads();
+        bool mine = false;
+        for (long long c = threadIdx.x; c < n; c += blockDim.x) {
+            if (!inside[c] || r[c]) continue;
+            const int x = (int)(c % nx), y = (int)(c / nx);
+            if ((x > 0 && r[c - 1]) || (x < nx - 1 && r[c + 1]) || (y > 0 && r[c - nx]) || (y < ny - 1 && r[c + nx])) {
+                r[c] = 1;
+                mine = true;
+            }
+        }
+        if (mine) changed = 1;
+        __syncthreads();
+        if (!changed) break;
     }
 }
 

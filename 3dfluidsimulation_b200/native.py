@@ -25,7 +25,7 @@ JACOBI, RED_BLACK = 0, 1
 
 EXPORTS = [
     "fs_abi_version", "fs_create", "fs_destroy", "fs_reset", "fs_last_error", "fs_slab_range",
-    "fs_set_obstacles", "fs_add_density", "fs_add_velocity", "fs_add_source_cells", "fs_add_sources",
+    "fs_set_obstacles", "fs_slab_halo_range", "fs_set_obstacles_slab", "fs_build_obstacles", "fs_get_obstacles", "fs_add_density", "fs_add_velocity", "fs_add_source_cells", "fs_add_sources",
     "fs_step", "fs_sync", "fs_get_field", "fs_set_field", "fs_get_field_async", "fs_wait_transfers", "fs_get_metrics",
     "fs_render_rgba", "fs_streamlines",
     "fs_op_set_bnd", "fs_op_diffuse", "fs_op_smooth", "fs_op_lin_solve", "fs_op_project", "fs_op_advect",
@@ -79,6 +79,18 @@ class FsVisParams(C.Structure):
         return v
 
 
+class FsObstacleShape(C.Structure):
+    """fs_obstacle_shape (include/fluidsolver.h): parameters of the device-side SetupObstacles (FluidSim.cs:302-388)."""
+    _fields_ = [
+        ("kind", C.c_int32), ("center_x", C.c_float), ("center_y", C.c_float), ("center_z", C.c_float),
+        ("radius", C.c_float), ("width", C.c_float), ("height", C.c_float), ("depth", C.c_float),
+        ("seed_x", C.c_int32), ("seed_y", C.c_int32), ("seed_z", C.c_int32), ("reserved", C.c_int32 * 3),
+    ]
+
+
+SHAPE_KINDS = {"Circle": 0, "Rectangle": 1, "Airfoil": 2}
+
+
 class FluidSolverError(RuntimeError):
     def __init__(self, code: int, message: str):
         super().__init__(f"fluidsolver error {code}: {message}")
@@ -108,6 +120,10 @@ def load(path: str | None = None) -> C.CDLL:
         "fs_last_error": (C.c_char_p, [vp]),
         "fs_slab_range": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64)]),
         "fs_set_obstacles": (C.c_int, [vp, vp, i64]),
+        "fs_slab_halo_range": (C.c_int, [vp, C.POINTER(i32), C.POINTER(i32)]),
+        "fs_set_obstacles_slab": (C.c_int, [vp, vp, i64, i32, i32]),
+        "fs_build_obstacles": (C.c_int, [vp, C.POINTER(FsObstacleShape), C.POINTER(i64)]),
+        "fs_get_obstacles": (C.c_int, [vp, vp, i64]),
         "fs_add_density": (C.c_int, [vp, f32, f32, f32, f32]),
         "fs_add_velocity": (C.c_int, [vp, f32, f32, f32, f32, f32, f32]),
         "fs_add_source_cells": (C.c_int, [vp, i64, vp, vp, vp, vp, vp, vp, vp]),
@@ -212,6 +228,28 @@ class NativeSolver:
     def set_obstacles(self, mask: np.ndarray):
         mask = np.ascontiguousarray(mask, dtype=np.uint8)
         self._ck(self.lib.fs_set_obstacles(self.h, mask.ctypes.data, mask.size))
+
+    def halo_range(self):
+        """Global planes [z0, z1) this handle holds (owned planes plus ghost planes)."""
+        z0, z1 = C.c_int32(), C.c_int32()
+        self._ck(self.lib.fs_slab_halo_range(self.h, C.byref(z0), C.byref(z1)))
+        return z0.value, z1.value
+
+    def set_obstacles_slab(self, mask: np.ndarray, global_any: bool, global_interior: bool):
+        """Mask of the planes halo_range() reports only (no rank needs the global mask)."""
+        mask = np.ascontiguousarray(mask, dtype=np.uint8)
+        self._ck(self.lib.fs_set_obstacles_slab(self.h, mask.ctypes.data, mask.size, int(global_any), int(global_interior)))
+
+    def build_obstacles(self, shape: "FsObstacleShape") -> int:
+        """Device-side SetupObstacles: builds this handle's planes of the mask; returns the global obstacle cell count."""
+        n = C.c_int64()
+        self._ck(self.lib.fs_build_obstacles(self.h, C.byref(shape), C.byref(n)))
+        return int(n.value)
+
+    def get_obstacles(self) -> np.ndarray:
+        out = np.empty(self.shape, np.uint8)
+        self._ck(self.lib.fs_get_obstacles(self.h, out.ctypes.data, out.size))
+        return out
 
     def add_density(self, x, y, z, amount):
         self._ck(self.lib.fs_add_density(self.h, x, y, z, amount))

@@ -106,37 +106,68 @@ class FluidSimulation:
             return abs(ny_) <= half
         return False
 
-    def SetupObstacles(self):
-        n = self.currentSize
+    def obstacle_shape(self):
+        """The reference's shape parameters in cells, computed as SetupObstacles / IsInsideShape compute them
+        (:308-324, :355-370), for the native mask builder (fs_build_obstacles)."""
+        n, nz = self.currentSize, self.currentDepth
+        sh = native.FsObstacleShape()
+        sh.kind = native.SHAPE_KINDS[self.obstacleShape]
+        sh.center_x, sh.center_y = f32(self.obstaclePositionX) * f32(n), f32(self.obstaclePositionY) * f32(n)
+        sh.center_z = f32(self.obstaclePositionZ) * f32(nz)
+        sh.radius = f32(self.obstacleRadius) * f32(n)
+        sh.width, sh.height = f32(self.obstacleWidth) * f32(n), f32(self.obstacleHeight) * f32(n)
+        sh.depth = f32(self.obstacleWidth) * f32(nz)          # 3D extension: the extrusion spans obstacleWidth of the depth
+        sh.seed_x, sh.seed_y = _round_half_even(self.obstaclePositionX * n), _round_half_even(self.obstaclePositionY * n)
+        sh.seed_z = _round_half_even(self.obstaclePositionZ * nz) if nz > 1 else 0
+        return sh
+
+    def reference_mask(self):
+        """SetupObstacles on the HOST, following the reference line by line (:302-388): the recursive 4-neighbour flood
+        fill (iterative here) over IsInsideShape; 3D: sphere / extruded cross-section as include/fluidsolver.h states.
+        Used by the tests as the restatement the device builder is checked against."""
+        n, nz = self.currentSize, self.currentDepth
+        sh = self.obstacle_shape()
         m2 = np.zeros((n, n), np.uint8)
-        if self.enableObstacle:
-            sx, sy = _round_half_even(self.obstaclePositionX * n), _round_half_even(self.obstaclePositionY * n)
-            size = (self.obstacleRadius if self.obstacleShape == "Circle" else self.obstacleWidth) * n  # :316-324
-            todo = deque([(sx, sy)])  # iterative form of the recursive 4-neighbour flood fill
-            while todo:
-                x, y = todo.pop()
-                if x < 0 or x >= n or y < 0 or y >= n or m2[y, x] or not self._inside(x, y, size):
-                    continue
-                m2[y, x] = 1
-                todo.extend(((x + 1, y), (x - 1, y), (x, y + 1), (x, y - 1)))
-        if self.currentDepth == 1:
-            self.obstacles = m2
-        else:
-            # 3D extension: circle -> sphere, other shapes extruded in z
-            nz = self.currentDepth
-            m3 = np.zeros((nz, n, n), np.uint8)
-            if self.enableObstacle:
-                if self.obstacleShape == "Circle":
-                    r = f32(self.obstacleRadius * n)
-                    z, y, x = np.meshgrid(np.arange(nz, dtype=f32), np.arange(n, dtype=f32), np.arange(n, dtype=f32), indexing="ij")
-                    cx, cy, cz = f32(self.obstaclePositionX * n), f32(self.obstaclePositionY * n), f32(self.obstaclePositionZ * nz)
-                    m3 = (((x - cx) ** 2 + (y - cy) ** 2 + (z - cz) ** 2) < r * r).astype(np.uint8)
-                else:
-                    half = max(1, int(self.obstacleWidth * nz * 0.5))
-                    c = _round_half_even(self.obstaclePositionZ * nz)
-                    m3[max(c - half, 0):min(c + half, nz)] = m2
-            self.obstacles = m3
-        self.native.set_obstacles(self.obstacles)
+        if not self.enableObstacle:
+            return m2 if nz == 1 else np.zeros((nz, n, n), np.uint8)
+        size = (self.obstacleRadius if self.obstacleShape == "Circle" else self.obstacleWidth) * n  # :316-324
+        todo = deque([(sh.seed_x, sh.seed_y)])
+        while todo:
+            x, y = todo.pop()
+            if x < 0 or x >= n or y < 0 or y >= n or m2[y, x] or not self._inside(x, y, size):
+                continue
+            m2[y, x] = 1
+            todo.extend(((x + 1, y), (x - 1, y), (x, y + 1), (x, y - 1)))
+        if nz == 1:
+            return m2
+        m3 = np.zeros((nz, n, n), np.uint8)
+        if not (0 <= sh.seed_z < nz):
+            return m3
+        if self.obstacleShape == "Circle":
+            cx, cy, cz, r = f32(sh.center_x), f32(sh.center_y), f32(sh.center_z), f32(sh.radius)
+            z, y, x = np.meshgrid(np.arange(nz, dtype=f32), np.arange(n, dtype=f32), np.arange(n, dtype=f32), indexing="ij")
+            d2 = ((x - cx) * (x - cx) + (y - cy) * (y - cy)) + (z - cz) * (z - cz)
+            inside = d2 < r * r
+            if inside[sh.seed_z, sh.seed_y, sh.seed_x] if (0 <= sh.seed_x < n and 0 <= sh.seed_y < n) else False:
+                m3 = inside.astype(np.uint8)
+            return m3
+        half = f32(sh.depth) * f32(0.5)
+        zs = np.arange(nz, dtype=f32)
+        span = (zs > f32(sh.center_z) - half) & (zs < f32(sh.center_z) + half)
+        if span[sh.seed_z]:
+            m3[span] = m2
+        return m3
+
+    def SetupObstacles(self):
+        """:302-327.  The mask is built ON THE DEVICE (fs_build_obstacles); `obstacles` is read back for the callers
+        that look at it (the reference's UpdateVisualization reads the managed array, :765)."""
+        if not self.enableObstacle:
+            shape = (self.currentSize, self.currentSize) if self.currentDepth == 1 else (self.currentDepth, self.currentSize, self.currentSize)
+            self.obstacles = np.zeros(shape, np.uint8)
+            self.native.set_obstacles(self.obstacles)
+            return
+        self.obstacleCells = self.native.build_obstacles(self.obstacle_shape())
+        self.obstacles = self.native.get_obstacles()
 
     # ---- sources -----------------------------------------------------------------------------------
     def AddDensity(self, x, y, amount, z=0.0):  # :723-729
@@ -168,20 +199,24 @@ class FluidSimulation:
             self.native.add_source_cells(xs, ys, z, ds, ax or None, ay or None, None)
 
     def AddForceToArea(self, center, force, radius):
-        """:452-483 -- mouse drag: velocity with linear fall-off, density inside 0.3 r."""
+        """:452-483 -- mouse drag: velocity with linear fall-off, density inside 0.3 r.  fp32 throughout, as
+        Vector2.Distance and the C# float expressions evaluate; sent as ONE batched native call."""
         n = self.currentSize
-        cx, cy = center
+        cx, cy, radius = f32(center[0]), f32(center[1]), f32(radius)
+        fx, fy = f32(force[0]), f32(force[1])
         clamp = lambda v: min(max(v, 0), n - 1)
         xs, ys, ds, ax, ay = [], [], [], [], []
-        for x in range(clamp(int(cx - radius)), clamp(int(cx + radius)) + 1):
+        for x in range(clamp(int(cx - radius)), clamp(int(cx + radius)) + 1):          # :454-457, (int) truncates
             for y in range(clamp(int(cy - radius)), clamp(int(cy + radius)) + 1):
-                dist = f32(math.sqrt(f32((x - cx) ** 2 + (y - cy) ** 2)))
+                dx, dy = f32(x) - cx, f32(y) - cy
+                dist = f32(math.sqrt(f32(dx * dx + dy * dy)))                           # Vector2.Distance
                 if dist <= radius:
-                    fall = f32(1) - dist / f32(radius)
-                    xs.append(x); ys.append(y); ax.append(f32(force[0]) * fall); ay.append(f32(force[1]) * fall)
-                    ds.append(f32(self.sourceStrength) * fall if dist < radius * 0.3 else f32(0))
+                    fall = f32(1) - dist / radius
+                    xs.append(x); ys.append(y); ax.append(fx * fall); ay.append(fy * fall)
+                    ds.append(f32(self.sourceStrength) * fall if dist < radius * f32(0.3) else f32(0))
         if xs:
-            self.native.add_source_cells(xs, ys, None, ds, ax, ay, None)
+            z = [self.sourcePositionZ * self.currentDepth] * len(xs) if self.currentDepth > 1 else None
+            self.native.add_source_cells(xs, ys, z, ds, ax, ay, None)
 
     # ---- Simulate / Update, :390-450, :551-576 --------------------------------------------------------
     def effective_parameters(self):

@@ -91,6 +91,36 @@ int fs_slab_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end, int64_t 
  * blittable: pass byte[]. */
 int fs_set_obstacles(fs_solver *s, const uint8_t *mask, int64_t n);
 
+/* Same, for a handle that only knows its own slab (no rank needs the GLOBAL mask: 1 GiB at 1024^3): mask holds the
+ * planes [z0, z1) reported by fs_slab_halo_range (the owned planes plus the ghost planes), n = nx*ny*(z1-z0).
+ * global_any / global_interior: whether ANY slab has an obstacle cell / an obstacle cell off the domain ring -- every
+ * slab must pass the same values (they select which halo operations exist). */
+int fs_slab_halo_range(const fs_solver *s, int32_t *z_begin, int32_t *z_end);
+int fs_set_obstacles_slab(fs_solver *s, const uint8_t *mask, int64_t n, int32_t global_any, int32_t global_interior);
+
+/* ---- obstacle mask builder on the device: SetupObstacles + RecursiveFloodFill +
+ * IsInsideShape, FluidSim.cs:302-388, generalised to 3D.  Each handle builds ONLY its own slab; no mask crosses the ABI.
+ *   kind 0 Circle    (x-cx)^2 + (y-cy)^2 [+ (z-cz)^2 in 3D: a sphere] < radius^2                        :360-361
+ *   kind 1 Rectangle x, y strictly inside center +- width/2, height/2 [3D: and z inside center_z +- depth/2: a box] :363-367
+ *   kind 2 Airfoil   the reference's NACA-0015 approximation, chord = 2*width [3D: extruded over depth]  :369-383
+ * and the reference's 4-neighbour flood fill from the seed cell (RoundToInt(position*size), :308-309): only cells
+ * of the shape that are connected to the seed become obstacles (nothing if the seed itself is outside).  In 3D the
+ * fill runs on the xy cross-section and is extruded (Rectangle / Airfoil); a sphere is its own fill.
+ * All lengths are in cells, computed by the host exactly as the reference does (obstacleRadius * currentSize, ...). */
+typedef struct fs_obstacle_shape {
+    int32_t kind;
+    float center_x, center_y, center_z; /* obstaclePositionX/Y * currentSize (:355-356); Z: * depth */
+    float radius;                        /* Circle: obstacleRadius * currentSize (:316) */
+    float width, height;                 /* obstacleWidth * currentSize, obstacleHeight * currentSize */
+    float depth;                         /* 3D Rectangle / Airfoil: extent in z, cells; ignored otherwise */
+    int32_t seed_x, seed_y, seed_z;      /* flood fill start */
+    int32_t reserved[3];                 /* must be 0 */
+} fs_obstacle_shape;
+/* obstacle_cells (may be NULL): number of obstacle cells of the GLOBAL grid. */
+int fs_build_obstacles(fs_solver *s, const fs_obstacle_shape *shape, int64_t *obstacle_cells);
+/* The mask of this handle's OWNED planes as the device holds it (n = owned voxels): what UpdateVisualization reads (:765). */
+int fs_get_obstacles(fs_solver *s, uint8_t *out, int64_t n);
+
 /* ---- sources: AddDensity / AddVelocity, FluidSim.cs:723-738 (cell = clamp((int)coord)) --------
  * Global coordinates; a handle ignores cells outside its slab.  z, az ignored when nz == 1. */
 int fs_add_density(fs_solver *s, float x, float y, float z, float amount);

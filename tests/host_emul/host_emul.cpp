@@ -21,6 +21,7 @@
 
 struct HostExec {
     bool use_graph = false;
+    bool pair_force = false;
     int64_t launches = 0;
     std::string msg;
     std::chrono::steady_clock::time_point t0;
@@ -66,7 +67,7 @@ struct HostExec {
     // Fused two-stage sweep, emulated with the per-cell functions and LOCAL data only (so that the CPU tier checks the
     // two-plane halo logic): stage 1 on the owned interior planes plus one plane each side into a scratch copy of
     // `in`, stage 2 on the owned interior planes.  FS_EMUL_NO_PAIR=1 makes the orchestration fall back to single sweeps.
-    bool pair_supported(const FsGrid &g, float) const {
+    bool pair_supported(const FsGrid &g, float, int /*kind*/) const {
         const char *e = getenv("FS_EMUL_NO_PAIR");
         return g.hz && !(e && e[0] == '1');
     }
@@ -78,7 +79,7 @@ struct HostExec {
     }
     bool relax_pair(int kind, const FsGrid &g, const float *in, const float *rhs, float *out, const uint8_t *flags,
                     float a, float c, int b, bool in_zero, bool fuse_halo) {
-        if (!pair_supported(g, c)) return false;
+        if (!pair_supported(g, c, kind)) return false;
         const int zb = g.zoff + g.kb, ze = g.zoff + g.ke;
         const int k0 = (zb < 1 ? 1 : zb) - g.zoff, k1 = (ze > g.nz - 1 ? g.nz - 1 : ze) - g.zoff; // owned interior [k0, k1)
         if (k1 <= k0) return true;
@@ -177,10 +178,77 @@ struct HostExec {
     void axpy(float *dst, const float *src, long long n) {
         for (long long t = 0; t < n; t++) dst[t] += src[t];
     }
-    void scatter_add(float *dst[4], const long long *idx, const float *src[4], long long n) {
+    std::vector<long long> stage_idx;
+    std::vector<float> stage_amt[4];
+    bool source_stage(long long cap, long long **idx, float *amt[4]) {
+        stage_idx.resize((size_t)cap);
+        *idx = stage_idx.data();
+        for (int f = 0; f < 4; f++) { stage_amt[f].resize((size_t)cap); amt[f] = stage_amt[f].data(); }
+        return true;
+    }
+    void scatter_add_staged(float *dst[4], long long, long long n) {
         for (long long t = 0; t < n; t++)
             for (int f = 0; f < 4; f++)
-                if (dst[f]) dst[f][idx[t]] += src[f][t];
+                if (dst[f]) dst[f][stage_idx[t]] += stage_amt[f][t];
+    }
+    bool scan_obstacles(const FsGrid &g, const uint8_t *mask, int kl0, int kl1, bool *any_local, long long **list, long long *count) {
+        std::vector<long long> v;
+        bool any = false;
+        for (long long t = g.sz * g.nzl - 1; t >= 0; t--) { // reversed on purpose: the list order must not matter
+            if (!mask[t]) continue;
+            any = true;
+            const int i = (int)(t % g.nx), j = (int)((t / g.nx) % g.ny), kl = (int)(t / g.sz);
+            if (i >= 1 && i <= g.nx - 2 && j >= 1 && j <= g.ny - 2 && kl >= kl0 && kl < kl1) v.push_back(t);
+        }
+        *any_local = any;
+        *count = (long long)v.size();
+        *list = nullptr;
+        if (!v.empty()) {
+            *list = (long long *)malloc(sizeof(long long) * v.size());
+            memcpy(*list, v.data(), sizeof(long long) * v.size());
+        }
+        return true;
+    }
+    bool build_shape(const FsGrid &g, const fs_obstacle_shape &sh, uint8_t *mask, long long *total, long long *interior) {
+        const int nx = g.nx, ny = g.ny, nz = g.nz;
+        const bool hz = g.hz != 0;
+        std::vector<uint8_t> inside((size_t)g.sz, 0), reach((size_t)g.sz, 0);
+        const bool need_fill = !(sh.kind == 0 && hz);
+        const bool seed_in_grid = sh.seed_x >= 0 && sh.seed_x < nx && sh.seed_y >= 0 && sh.seed_y < ny && (!hz || (sh.seed_z >= 0 && sh.seed_z < nz));
+        bool seed_ok;
+        if (need_fill) {
+            for (int y = 0; y < ny; y++)
+                for (int x = 0; x < nx; x++)
+                    inside[x + (size_t)y * nx] = sh.kind == 0 ? fs_shape_inside_circle(sh, false, x, y, 0) : fs_shape_inside_xy(sh, x, y);
+            if (seed_in_grid) { // RecursiveFloodFill :329-351 with an explicit stack
+                std::vector<std::pair<int, int>> todo{{sh.seed_x, sh.seed_y}};
+                while (!todo.empty()) {
+                    const auto [x, y] = todo.back();
+                    todo.pop_back();
+                    if (x < 0 || x >= nx || y < 0 || y >= ny || reach[x + (size_t)y * nx] || !inside[x + (size_t)y * nx]) continue;
+                    reach[x + (size_t)y * nx] = 1;
+                    todo.emplace_back(x + 1, y); todo.emplace_back(x - 1, y); todo.emplace_back(x, y + 1); todo.emplace_back(x, y - 1);
+                }
+            }
+            seed_ok = seed_in_grid && fs_shape_in_span(sh, hz && sh.kind != 0, sh.seed_z);
+        } else {
+            seed_ok = seed_in_grid && fs_shape_inside_circle(sh, true, sh.seed_x, sh.seed_y, sh.seed_z);
+        }
+        for (int kl = 0; kl < g.nzl; kl++)
+            for (int y = 0; y < ny; y++)
+                for (int x = 0; x < nx; x++)
+                    mask[fs_idx(g, x, y, kl)] = seed_ok ? fs_shape_mask(sh, hz, nx, reach.data(), seed_ok, x, y, kl + g.zoff) : 0;
+        long long tot = 0, inter = 0;
+        for (int z = 0; z < nz; z++)
+            for (int y = 0; y < ny; y++)
+                for (int x = 0; x < nx; x++) {
+                    if (!seed_ok || !fs_shape_mask(sh, hz, nx, reach.data(), seed_ok, x, y, z)) continue;
+                    tot++;
+                    if (x >= 1 && x <= nx - 2 && y >= 1 && y <= ny - 2 && (!hz || (z >= 1 && z <= nz - 2))) inter++;
+                }
+        *total = tot;
+        *interior = inter;
+        return true;
     }
     void metrics(const FsGrid &g, const float *d, const float *ux, const float *uy, const float *uz, double *sum, float *mx) {
         double acc = 0;

@@ -213,7 +213,7 @@ def test_vector_and_scalar_kernels_agree(lib, oracle):
     minutes for: 256^3, full step, bit-identical fields."""
     def run(force, no_pair=False):
         os.environ["FS_FORCE_GENERIC"] = "1" if force else "0"
-        os.environ["FS_NO_PAIR"] = "1" if no_pair else "0"
+        os.environ["FS_PAIR"] = "0" if no_pair else "1"      # 1: fuse wherever the kernel applies (the default policy is auto)
         try:
             s, _ = None, None
             pk = P.pkg()
@@ -228,7 +228,7 @@ def test_vector_and_scalar_kernels_agree(lib, oracle):
             return out
         finally:
             os.environ.pop("FS_FORCE_GENERIC", None)
-            os.environ.pop("FS_NO_PAIR", None)
+            os.environ.pop("FS_PAIR", None)
     a, b, c = run(False), run(True), run(False, no_pair=True)
     for n in a:
         P.assert_exact(a[n], b[n], f"fused/vec4 vs per-cell {n}")
@@ -237,7 +237,7 @@ def test_vector_and_scalar_kernels_agree(lib, oracle):
 
 @pytest.mark.parametrize("kind", ["jacobi", "smooth", "rb"])
 @pytest.mark.parametrize("dims", [(64, 40, 35), (132, 20, 70), (8, 3, 3), (4, 3, 3), (256, 100, 9), (16, 12, 9)])
-def test_fused_pair_kernel_vs_oracle(lib, oracle, kind, dims):
+def test_fused_pair_kernel_vs_oracle(lib, oracle, kind, dims, monkeypatch):
     """The fused two-stage sweep (two Jacobi / smoother iterations or both red-black colours per pass) against the
     oracle for every field kind b it is used for (b = 0 with obstacles; b = 1, 2, 3 without), odd iteration counts
     (pair + single mix) and tile shapes that leave partial tiles in x, y and z."""
@@ -246,6 +246,7 @@ def test_fused_pair_kernel_vs_oracle(lib, oracle, kind, dims):
     shape = (nz, ny, nx)
     x0, guess = P.rnd(shape, rng), P.rnd(shape, rng)
     a, c = np.float32(0.37), np.float32(1 + 6 * 0.37)
+    monkeypatch.setenv("FS_PAIR", "1")   # read at fs_create: fuse wherever the kernel applies (default: auto policy)
     for obstacles, bs in ((True, (0,)), (False, (0, 1, 2, 3))):
         mask = P.random_mask(shape, rng) if obstacles else np.zeros(shape, np.uint8)
         with P.make_solver(lib, nx, ny, nz) as s:
