@@ -6,10 +6,12 @@ The package name starts with a digit, so import it with
 
 Contents: ``csrc/`` (kernels + C ABI, built into ``libfluidsolver.so`` by ``build.py``),
 ``native`` (ctypes binding, no CPU fallback), ``solver`` (host-side mirror of the reference's
-``FluidSimulation`` surface), ``slab`` (z-slab partitioning for multi-GPU runs).
+``FluidSimulation`` surface), ``slab`` (z-slab partitioning for multi-GPU runs), ``runlog`` (portable
+run-parameter / metrics sink replacing the reference's SQL.cs).
 """
 from . import native  # noqa: F401
 from .native import FluidSolverError, NativeSolver  # noqa: F401
+from .runlog import RunLog  # noqa: F401
 from .solver import FluidSimulation  # noqa: F401
 
-__all__ = ["native", "NativeSolver", "FluidSimulation", "FluidSolverError"]
+__all__ = ["native", "NativeSolver", "FluidSimulation", "FluidSolverError", "RunLog"]

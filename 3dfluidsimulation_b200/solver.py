@@ -54,6 +54,7 @@ class FluidSimulation:
         self.itersDiffuse, self.itersPressure, self.solverKind = itersDiffuse, itersPressure, solverKind
         self._device_id, self._use_graph, self._lib_path = device_id, use_cuda_graph, lib_path
         self.elapsedTime = 0.0
+        self.runLog, self._currentRunID, self._smoothedFPS = None, -1, 0.0
         self.native: native.NativeSolver | None = None
         self.ResetSimulation()
 
@@ -233,13 +234,37 @@ class FluidSimulation:
     Step = Simulate
 
     def Update(self, deltaTime=1.0 / 60):
-        """:390-450 without input/visualisation: sources first, then the step."""
+        """:390-450 without input/visualisation: sources first, then the step (+ LogCurrentMetrics :572-575 when a
+        run log is attached)."""
         if self.paused:
             return
         self.elapsedTime += deltaTime
         if self.enableCustomSource:
             self.UpdateCustomSource()
         self.Simulate()
+        if self.runLog is not None and self._currentRunID != -1:
+            self.LogCurrentMetrics(deltaTime)
+
+    # ---- persistence (SQL.cs through the portable sink, runlog.py) ---------------------------------------------
+    def AttachRunLog(self, log):
+        """Start(): `_currentRunID = SQL.SaveSimRunParams(...)` (:205); metrics follow every step (:572-575)."""
+        self.runLog = log
+        self._currentRunID = self.SaveCurrentConfiguration()
+        return self._currentRunID
+
+    def SaveCurrentConfiguration(self):  # :2004-2022
+        if self.runLog is None:
+            return -1
+        return self.runLog.save_sim_run_params(
+            self.size, self.diffusion, self.viscosity, self.timeStep, self.enableCustomSource, self.sourceStrength,
+            self.sourcePositionX, self.sourcePositionY, self.enableObstacle, self.obstacleShape, self.obstaclePositionX,
+            self.obstaclePositionY, self.obstacleRadius, self.obstacleWidth, self.obstacleHeight)
+
+    def LogCurrentMetrics(self, deltaTime):  # :578-615: two device reductions instead of two host loops over the fields
+        mean, mx = self.metrics()
+        self._smoothedFPS = 0.9 * self._smoothedFPS + 0.1 * (1.0 / deltaTime)   # CalculateFrameRate :609-615
+        if mx != 0 and mean != 0:                                                    # :597
+            self.runLog.log_runtime_metrics(self._currentRunID, 0, mean, mx, self._smoothedFPS)
 
     # ---- readers (what UpdateVisualization/LogCurrentMetrics pull, :587-594, :761-768) -------------------
     def field(self, name):

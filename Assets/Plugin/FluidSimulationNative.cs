@@ -5,9 +5,10 @@
 // All numerical work happens in libfluidsolver.so (CUDA, sm_100a) behind NativeFluidSolver.cs; this class
 // only does what the reference does on the managed side: parameter scaling (FluidSim.cs:216-222, :554-556),
 // source discs (:485-533, :452-483), the obstacle mask (:302-388) and the per-frame call order (:390-450).
-// Rendering, input and SQLite logging stay in the reference's own scripts: they read the public arrays
-// Density / Pressure / VelocityX / VelocityY that Update() refreshes (what UpdateVisualization and
-// DrawStreamlines read from the private fields in the reference, :761-768, :919-920).
+// The per-frame consumers run on the device as well: UpdateVisualization (:755-866) is fs_render_rgba straight into the
+// Color[] the reference fills, DrawStreamlines (:886-959) is fs_streamlines + the reference's host-side Bresenham
+// drawing (:1765-1849), LogCurrentMetrics (:578-607) is fs_get_metrics; SetupObstacles (:302-388) is
+// fs_build_obstacles.  No full field crosses the boundary in a frame; ReadFields() fetches them on demand.
 //
 // NOT compiled in the build container (no C#/Unity toolchain).  The Python mirror
 // 3dfluidsimulation_b200/solver.py has the same logic and is what the tests drive.
@@ -55,6 +56,33 @@ public class FluidSimulationNative : MonoBehaviour
     [Range(0.01f, 0.5f)] public float obstacleRadius = 0.1f;
     [Range(0.01f, 0.5f)] public float obstacleWidth = 0.2f;
     [Range(0.01f, 0.5f)] public float obstacleHeight = 0.2f;
+    [Range(0f, 1f)] public float obstaclePositionZ = 0.5f;   // 3D extension
+    public Color obstacleColor = Color.gray;
+
+    [Header("Visualization")]            // FluidSim.cs:57-95
+    public enum ColorMode { SingleColor, Gradient, DensityBased, PressureBased, Streamlines }
+    public ColorMode colorMode = ColorMode.SingleColor;
+    public Color fluidcolour = Color.white;
+    [Range(0f, 1f)] public float colourIntensity = 1f;
+    public Gradient colourGradient;
+    public bool useLerp = false;
+    public Color startColor = Color.white, endColor = Color.white;
+    public Color lowPressureColor = Color.blue, neutralPressureColor = Color.white, highPressureColor = Color.red;
+    public float lowPressureThreshold = -50f, highPressureThreshold = 50f;
+    public Color lowDensityColor = Color.blue, mediumDensityColor = Color.green, highDensityColor = Color.red;
+    [Range(0f, 500f)] public float mediumDensityThreshold = 50f;
+    [Range(0f, 1000f)] public float highDensityThreshold = 200f;
+    public bool visualizeSourcePosition = true;
+    public Color sourcePositionColor = Color.yellow;
+    public bool showStreamlines = false;
+    [Range(1f, 5f)] public int streamlineDensity = 4;
+    [Range(1f, 10f)] public float streamlineScale = 1.0f;
+    public Color streamlineColor = Color.white;
+    [Range(0.1f, 3f)] public float streamlineThickness = 1.0f;
+    [Tooltip("3D extension: the z plane that is rendered (normalised)")] [Range(0f, 1f)] public float viewSliceZ = 0.5f;
+    public bool moveSourceWithMouse = false;
+    public KeyCode sourcePositionKey = KeyCode.LeftShift;
+    public Texture2D fluidTexture, streamlineTexture;
 
     // what the visualisation / metrics code reads each frame
     public float[] Density, Pressure, VelocityX, VelocityY;
@@ -106,48 +134,26 @@ public class FluidSimulationNative : MonoBehaviour
         SetupObstacles();
     }
 
-    // SetupObstacles / flood fill (FluidSim.cs:302-388), iterative instead of recursive; 3D: the 2D mask extruded
+    // SetupObstacles (FluidSim.cs:302-327): the flood fill over IsInsideShape runs on the device (fs_build_obstacles);
+    // only the shape parameters, computed as the reference computes them (:308-324, :355-370), cross the boundary.
     public void SetupObstacles()
     {
         int n = currentSize;
-        var plane = new byte[n * n];
-        if (enableObstacle)
-        {
-            float extent = (obstacleShape == ObstacleShape.Circle ? obstacleRadius : obstacleWidth) * n;
-            var todo = new Stack<Vector2Int>();
-            todo.Push(new Vector2Int(Mathf.RoundToInt(obstaclePositionX * n), Mathf.RoundToInt(obstaclePositionY * n)));
-            while (todo.Count > 0)
-            {
-                var c = todo.Pop();
-                if (c.x < 0 || c.x >= n || c.y < 0 || c.y >= n || plane[c.x + c.y * n] != 0 || !InsideShape(c.x, c.y, extent)) continue;
-                plane[c.x + c.y * n] = 1;
-                todo.Push(new Vector2Int(c.x + 1, c.y)); todo.Push(new Vector2Int(c.x - 1, c.y));
-                todo.Push(new Vector2Int(c.x, c.y + 1)); todo.Push(new Vector2Int(c.x, c.y - 1));
-            }
-        }
         Obstacles = new byte[n * n * currentDepth];
-        for (int k = 0; k < currentDepth; k++) Array.Copy(plane, 0, Obstacles, k * n * n, n * n);
-        Native.Check(Native.fs_set_obstacles(solver, Obstacles, Obstacles.Length), solver);
-    }
-
-    bool InsideShape(int x, int y, float extent)
-    {
-        float cx = obstaclePositionX * currentSize, cy = obstaclePositionY * currentSize;
-        switch (obstacleShape)
+        if (!enableObstacle) { Native.Check(Native.fs_set_obstacles(solver, Obstacles, Obstacles.Length), solver); return; }
+        var shape = new FsObstacleShape
         {
-            case ObstacleShape.Circle:
-                return (x - cx) * (x - cx) + (y - cy) * (y - cy) < extent * extent;
-            case ObstacleShape.Rectangle:
-                float hw = obstacleWidth * currentSize * 0.5f, hh = obstacleHeight * currentSize * 0.5f;
-                return x > cx - hw && x < cx + hw && y > cy - hh && y < cy + hh;
-            default: // NACA 0015 approximation, FluidSim.cs:369-383
-                float chord = 2 * obstacleWidth * currentSize, t = 0.15f;
-                float u = (x - cx + chord / 2) / chord, v = (y - cy) / chord;
-                if (u < 0 || u > 1 || Math.Abs(v) > t) return false;
-                float half = 5 * t * (0.2969f * Mathf.Sqrt(u) - 0.1260f * u - 0.3516f * u * u + 0.2843f * u * u * u - 0.1015f * u * u * u * u);
-                return Math.Abs(v) <= half;
-        }
+            kind = (int)obstacleShape,
+            centerX = obstaclePositionX * n, centerY = obstaclePositionY * n, centerZ = obstaclePositionZ * currentDepth,
+            radius = obstacleRadius * n, width = obstacleWidth * n, height = obstacleHeight * n,
+            depth = obstacleWidth * currentDepth,
+            seedX = Mathf.RoundToInt(obstaclePositionX * n), seedY = Mathf.RoundToInt(obstaclePositionY * n),
+            seedZ = currentDepth > 1 ? Mathf.RoundToInt(obstaclePositionZ * currentDepth) : 0
+        };
+        Native.Check(Native.fs_build_obstacles(solver, ref shape, out ObstacleCells), solver);
+        Native.Check(Native.fs_get_obstacles(solver, Obstacles, Obstacles.Length), solver);
     }
+    public long ObstacleCells;
 
     // AddDensity / AddVelocity (FluidSim.cs:723-738): the native side truncates and clamps like the reference
     public void AddDensity(float x, float y, float amount, float z = 0f) { Native.Check(Native.fs_add_density(solver, x, y, z, amount), solver); }
@@ -187,13 +193,145 @@ public class FluidSimulationNative : MonoBehaviour
         Native.Check(Native.fs_step(solver, dt, visc, diff), solver);
     }
 
-    // Update (FluidSim.cs:390-450): sources, step, then the fields the visualisation reads
+    // AddForceToArea (FluidSim.cs:452-483): velocity with linear fall-off, density inside 0.3 r -- ONE batched native call
+    public void AddForceToArea(Vector2 center, Vector2 force, float radius)
+    {
+        int minX = Mathf.Clamp((int)(center.x - radius), 0, currentSize - 1), maxX = Mathf.Clamp((int)(center.x + radius), 0, currentSize - 1);
+        int minY = Mathf.Clamp((int)(center.y - radius), 0, currentSize - 1), maxY = Mathf.Clamp((int)(center.y + radius), 0, currentSize - 1);
+        sx.Clear(); sy.Clear(); sz.Clear(); sd.Clear(); sax.Clear(); say.Clear();
+        for (int x = minX; x <= maxX; x++)
+            for (int y = minY; y <= maxY; y++)
+            {
+                float distance = Vector2.Distance(new Vector2(x, y), center);
+                if (distance > radius) continue;
+                float falloff = 1 - (distance / radius);
+                sx.Add(x); sy.Add(y); sz.Add(sourcePositionZ * currentDepth);
+                sax.Add(force.x * falloff); say.Add(force.y * falloff);
+                sd.Add(distance < radius * 0.3f ? sourceStrength * falloff : 0f);
+            }
+        if (sx.Count == 0) return;
+        Native.Check(Native.fs_add_source_cells(solver, sx.Count, sx.ToArray(), sy.ToArray(), sz.ToArray(), sd.ToArray(),
+            sax.ToArray(), say.ToArray(), null), solver);
+    }
+
+    private Vector2 _prevMouseGridPos;
+    private bool _isFirstDragFrame = true;
+    public Func<Vector2> MousePositionInGrid;   // GetMousePositionInGrid (:535-549) stays with the scene's quad/camera code
+
+    // Update (FluidSim.cs:390-450): source, mouse drag, Simulate, UpdateVisualization -- the reference's order
     void Update()
     {
         if (paused) return;
         elapsedTime += Time.deltaTime;
+        Vector2 mouse = MousePositionInGrid != null ? MousePositionInGrid() : Vector2.zero;
+        bool positioning = moveSourceWithMouse && Input.GetKey(sourcePositionKey);
+        if (positioning) SetSourcePosition(mouse.x, mouse.y);
         if (enableCustomSource) UpdateCustomSource();
+        if (MousePositionInGrid != null && Input.GetMouseButton(0) && !positioning)
+        {
+            if (!_isFirstDragFrame)
+            {
+                Vector2 mouseDelta = mouse - _prevMouseGridPos;
+                float forceMagnitude = mouseDelta.magnitude * resolutionMultiplier;
+                float scaledForce = Mathf.Pow(forceMagnitude, 1.5f) * 0.8f;
+                AddForceToArea(mouse, mouseDelta.normalized * scaledForce, Mathf.Clamp(forceMagnitude * 0.5f, 2f, 10f));
+            }
+            _isFirstDragFrame = false;
+            _prevMouseGridPos = mouse;
+        }
+        else _isFirstDragFrame = true;
         Step();
+        UpdateVisualization();
+        if (showStreamlines && colorMode != ColorMode.Streamlines) CombineTextures();
+    }
+
+    // UpdateVisualization (FluidSim.cs:755-866): UpdateVisualizationJob runs on the device, one RGBA plane comes back
+    private Color[] colours;
+    public void UpdateVisualization()
+    {
+        int n = currentSize;
+        if (colours == null || colours.Length != n * n) colours = new Color[n * n];
+        if (fluidTexture == null || fluidTexture.width != n) { fluidTexture = new Texture2D(n, n, TextureFormat.RGBAFloat, false); fluidTexture.filterMode = FilterMode.Point; }
+        if (useLerp) fluidcolour = Color.Lerp(startColor, endColor, Mathf.PingPong(elapsedTime * 0.1f, 1f));   // :789-793
+        var vp = new FsVisParams
+        {
+            colorMode = (int)colorMode, visualizeSourcePosition = visualizeSourcePosition ? 1 : 0, enableCustomSource = enableCustomSource ? 1 : 0,
+            zSlice = currentDepth > 1 ? Mathf.Clamp(Mathf.RoundToInt(viewSliceZ * currentDepth), 0, currentDepth - 1) : 0,
+            sourceX = sourcePositionX * n, sourceY = sourcePositionY * n, visualMarkerRadius = 3f,                 // :805-807
+            colourIntensity = colourIntensity, mediumDensityThreshold = mediumDensityThreshold, highDensityThreshold = highDensityThreshold,
+            lowPressureThreshold = lowPressureThreshold, highPressureThreshold = highPressureThreshold,
+            fluidColor = fluidcolour, obstacleColor = obstacleColor, sourcePositionColor = sourcePositionColor,
+            lowDensityColor = lowDensityColor, mediumDensityColor = mediumDensityColor, highDensityColor = highDensityColor,
+            lowPressureColor = lowPressureColor, neutralPressureColor = neutralPressureColor, highPressureColor = highPressureColor,
+            gradientColors = new Color[8], gradientTimes = new float[8]
+        };
+        if (colorMode == ColorMode.Gradient && colourGradient != null)                                            // :770-787
+        {
+            GradientColorKey[] keys = colourGradient.colorKeys;
+            vp.gradientKeyCount = Mathf.Min(keys.Length, 8);
+            for (int i = 0; i < vp.gradientKeyCount; i++) { vp.gradientColors[i] = keys[i].color; vp.gradientTimes[i] = keys[i].time; }
+        }
+        Native.Check(Native.fs_render_rgba(solver, ref vp, colours, (long)n * n * 4), solver);
+        fluidTexture.SetPixels(colours);                                                                          // :849-850
+        fluidTexture.Apply();
+        if (showStreamlines || colorMode == ColorMode.Streamlines) DrawStreamlines();
+        if (colorMode == ColorMode.Streamlines) CombineTextures();
+    }
+
+    void CombineTextures()                                                                                        // :868-884
+    {
+        Color[] fluidColors = fluidTexture.GetPixels(), streamColors = streamlineTexture.GetPixels();
+        for (int i = 0; i < fluidColors.Length; i++) if (streamColors[i].a > 0) fluidColors[i] = streamColors[i];
+        fluidTexture.SetPixels(fluidColors);
+        fluidTexture.Apply();
+    }
+
+    // DrawStreamlines (FluidSim.cs:886-959): the two glyph jobs run on the device (fs_streamlines); Bresenham stays here
+    private float[] segments;
+    public void DrawStreamlines()
+    {
+        if (!showStreamlines && colorMode != ColorMode.Streamlines) return;
+        int n = currentSize;
+        int skip = Mathf.Max(1, n / (streamlineDensity * 10));
+        int count = (n / skip) * (n / skip);
+        if (streamlineTexture == null || streamlineTexture.width != n) { streamlineTexture = new Texture2D(n, n, TextureFormat.RGBA32, false); streamlineTexture.filterMode = FilterMode.Point; }
+        if (segments == null || segments.Length != count * 4) segments = new float[count * 4];
+        int z = currentDepth > 1 ? Mathf.Clamp(Mathf.RoundToInt(viewSliceZ * currentDepth), 0, currentDepth - 1) : 0;
+        Native.Check(Native.fs_streamlines(solver, skip, streamlineScale, z, segments, count), solver);
+        var colors = new Color[n * n];
+        for (int i = 0; i < count; i++)
+        {
+            if (segments[4 * i] < 0) continue;                                                                     // :1772
+            DrawBresenhamLine((int)segments[4 * i], (int)segments[4 * i + 1], (int)Math.Round(segments[4 * i + 2]), (int)Math.Round(segments[4 * i + 3]),
+                              colors, streamlineColor, n, streamlineThickness);
+        }
+        streamlineTexture.SetPixels(colors);
+        streamlineTexture.Apply();
+    }
+
+    static void DrawBresenhamLine(int x0, int y0, int x1, int y1, Color[] colors, Color lineColor, int size, float thickness) // :1783-1849
+    {
+        bool steep = Mathf.Abs(y1 - y0) > Mathf.Abs(x1 - x0);
+        if (steep) { int t = x0; x0 = y0; y0 = t; t = x1; x1 = y1; y1 = t; }
+        if (x0 > x1) { int t = x0; x0 = x1; x1 = t; t = y0; y0 = y1; y1 = t; }
+        int dx = x1 - x0, dy = Mathf.Abs(y1 - y0), error = dx / 2, y = y0, ystep = (y0 < y1) ? 1 : -1;
+        int halfThick = (int)Mathf.Floor(thickness / 2);
+        for (int x = x0; x <= x1; x++)
+        {
+            for (int tx = -halfThick; tx <= halfThick; tx++)
+                for (int ty = -halfThick; ty <= halfThick; ty++)
+                {
+                    int drawX = steep ? y + tx : x + tx, drawY = steep ? x + ty : y + ty;
+                    if (drawX >= 0 && drawX < size && drawY >= 0 && drawY < size) colors[drawX + drawY * size] = lineColor;
+                }
+            error -= dy;
+            if (error < 0) { y += ystep; error += dx; }
+        }
+    }
+
+    /// <summary>Full fields on demand (the reference keeps them in managed arrays; here they live on the device).</summary>
+    public void ReadFields()
+    {
         Native.Check(Native.fs_get_field(solver, (int)FsField.Density, Density, Density.Length), solver);
         Native.Check(Native.fs_get_field(solver, (int)FsField.Pressure, Pressure, Pressure.Length), solver);
     }

@@ -41,6 +41,45 @@ namespace FluidSolverNative
         public int slabRank, slabCount;
         public int useCudaGraph;
         public int reserved0, reserved1, reserved2, reserved3;
+        public const int NativeSize = 72;
+    }
+
+    /// <summary>fs_vis_params (include/fluidsolver.h): the parameters UpdateVisualization passes to UpdateVisualizationJob
+    /// (FluidSim.cs:799-829).  Field for field and in the same order as the C struct; NativeSize / offsets are checked
+    /// against a compiled C probe by tests/test_abi_and_host.py::test_csharp_struct_layouts.</summary>
+    [StructLayout(LayoutKind.Sequential)]
+    public struct FsVisParams
+    {
+        public const int NativeSize = 356;
+        public int colorMode;                 // offset 0   ColorMode: 0 SingleColor, 1 Gradient, 2 DensityBased, 3 PressureBased, 4 Streamlines
+        public int visualizeSourcePosition;   // offset 4
+        public int enableCustomSource;        // offset 8
+        public int gradientKeyCount;          // offset 12  0..8
+        public int zSlice;                    // offset 16
+        public float sourceX, sourceY;        // offset 20, 24   sourcePosition * currentSize
+        public float visualMarkerRadius;      // offset 28
+        public float colourIntensity;         // offset 32
+        public float mediumDensityThreshold, highDensityThreshold; // offset 36, 40
+        public float lowPressureThreshold, highPressureThreshold; // offset 44, 48
+        public Color fluidColor, obstacleColor, sourcePositionColor;        // offset 52, 68, 84   (Color = 4 floats r,g,b,a)
+        public Color lowDensityColor, mediumDensityColor, highDensityColor; // offset 100, 116, 132
+        public Color lowPressureColor, neutralPressureColor, highPressureColor; // offset 148, 164, 180
+        [MarshalAs(UnmanagedType.ByValArray, SizeConst = 8)] public Color[] gradientColors; // offset 196
+        [MarshalAs(UnmanagedType.ByValArray, SizeConst = 8)] public float[] gradientTimes;  // offset 324
+    }
+
+    /// <summary>fs_obstacle_shape: SetupObstacles / IsInsideShape parameters in cells (FluidSim.cs:302-388).</summary>
+    [StructLayout(LayoutKind.Sequential)]
+    public struct FsObstacleShape
+    {
+        public const int NativeSize = 56;
+        public int kind;                       // offset 0   0 Circle, 1 Rectangle, 2 Airfoil
+        public float centerX, centerY, centerZ; // offset 4, 8, 12
+        public float radius;                   // offset 16
+        public float width, height;            // offset 20, 24
+        public float depth;                    // offset 28
+        public int seedX, seedY, seedZ;        // offset 32, 36, 40
+        public int reserved0, reserved1, reserved2; // offset 44
     }
 
     public sealed class SolverHandle : SafeHandle
@@ -63,6 +102,11 @@ namespace FluidSolverNative
         [DllImport(Lib, CallingConvention = CC)] public static extern IntPtr fs_last_error(SolverHandle s);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_slab_range(SolverHandle s, out int zBegin, out int zEnd, out long ownedVoxels);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_set_obstacles(SolverHandle s, byte[] mask, long n);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_slab_halo_range(SolverHandle s, out int zBegin, out int zEnd);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_set_obstacles_slab(SolverHandle s, byte[] mask, long n, int globalAny, int globalInterior);
+        // device-side SetupObstacles + RecursiveFloodFill (FluidSim.cs:302-388): no mask crosses the boundary
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_build_obstacles(SolverHandle s, ref FsObstacleShape shape, out long obstacleCells);
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_obstacles(SolverHandle s, [Out] byte[] dst, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_density(SolverHandle s, float x, float y, float z, float amount);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_velocity(SolverHandle s, float x, float y, float z, float ax, float ay, float az);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_add_source_cells(SolverHandle s, long count, float[] x, float[] y, float[] z, float[] density, float[] ax, float[] ay, float[] az);
@@ -74,8 +118,8 @@ namespace FluidSolverNative
         // pipelined readback: dst must be pinned (GCHandle.Alloc(..., GCHandleType.Pinned)) until fs_wait_transfers returns
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_field_async(SolverHandle s, int field, IntPtr dst, long n);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_wait_transfers(SolverHandle s);
-        // device-side UpdateVisualizationJob: one xy plane as RGBA floats (Color[] layout); vp = fs_vis_params blob (see include/fluidsolver.h)
-        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_render_rgba(SolverHandle s, IntPtr visParams, [Out] Color[] outRgba, long n);
+        // device-side UpdateVisualizationJob: one xy plane as RGBA floats, straight into the Color[] the reference fills (:849)
+        [DllImport(Lib, CallingConvention = CC)] public static extern int fs_render_rgba(SolverHandle s, ref FsVisParams visParams, [Out] Color[] outRgba, long n);
         // device-side StreamlineCalculationJob + StreamlineDrawJob: count*4 floats (x0, y0, x1, y1), -1 = invalid glyph
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_streamlines(SolverHandle s, int skip, float scale, int zSlice, [Out] float[] segments, long count);
         [DllImport(Lib, CallingConvention = CC)] public static extern int fs_get_metrics(SolverHandle s, out float meanDensity, out float maxSpeed, out double sumDensity);

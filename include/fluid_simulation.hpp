@@ -4,9 +4,11 @@
 // C++17 class is the compilable twin of Assets/Plugin/FluidSimulationNative.cs: the same field names, the same
 // public methods (SetPaused, GetSourcePosition, SetSourcePosition) plus Step/AddDensity/AddVelocity, and the
 // managed-side logic of the reference (Assets/Scripts/FluidSim.cs): parameter scaling :216-222/:554-556, the
-// custom-source disc :485-533, the obstacle flood fill :302-388, the Update() order :390-450.
+// custom-source disc :485-533, AddForceToArea :452-483, the obstacle shape parameters :302-388, the Update() order
+// :390-450, and the per-frame consumers UpdateVisualization :755-866 / DrawStreamlines :886-959 (device jobs + host Bresenham).
 // Everything numerical happens behind fs_* (libfluidsolver.so on a B200; tests/host_emul on the CPU tier).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <stdexcept>
@@ -34,7 +36,15 @@ public:
     float sourcePositionX = 0.5f, sourcePositionY = 0.5f, sourcePositionZ = 0.5f;
     bool enableObstacle = true;
     ObstacleShape obstacleShape = ObstacleShape::Circle;
-    float obstaclePositionX = 0.5f, obstaclePositionY = 0.5f, obstacleRadius = 0.1f, obstacleWidth = 0.2f, obstacleHeight = 0.2f;
+    float obstaclePositionX = 0.5f, obstaclePositionY = 0.5f, obstaclePositionZ = 0.5f;
+    float obstacleRadius = 0.1f, obstacleWidth = 0.2f, obstacleHeight = 0.2f;
+    // visualisation (:57-95): the fields UpdateVisualization / DrawStreamlines pass to their jobs
+    int colorMode = 0; // ColorMode: 0 SingleColor, 1 Gradient, 2 DensityBased, 3 PressureBased, 4 Streamlines
+    float colourIntensity = 1.0f, mediumDensityThreshold = 50.0f, highDensityThreshold = 200.0f;
+    float lowPressureThreshold = -50.0f, highPressureThreshold = 50.0f;
+    bool visualizeSourcePosition = true;
+    int streamlineDensity = 4;
+    float streamlineScale = 1.0f, streamlineThickness = 1.0f, viewSliceZ = 0.5f;
     int itersDiffuse = 20, itersPressure = 20, solverKind = FS_JACOBI, deviceId = 0;
     bool useCudaGraph = true;
 
@@ -79,25 +89,98 @@ public:
         SetupObstacles();
     }
 
-    // SetupObstacles / RecursiveFloodFill / IsInsideShape, :302-388 (iterative flood fill; 3D: the 2D mask extruded)
+    // SetupObstacles, :302-327: RecursiveFloodFill over IsInsideShape runs on the device (fs_build_obstacles); only the
+    // shape parameters, computed as the reference computes them (:308-324, :355-370), cross the boundary.
     void SetupObstacles() {
         const int n = currentSize_;
-        std::vector<uint8_t> plane((size_t)n * n, 0);
-        if (enableObstacle) {
-            const float extent = (obstacleShape == ObstacleShape::Circle ? obstacleRadius : obstacleWidth) * n;
-            std::vector<std::pair<int, int>> todo;
-            todo.emplace_back((int)std::nearbyint(obstaclePositionX * n), (int)std::nearbyint(obstaclePositionY * n));
-            while (!todo.empty()) {
-                const auto [x, y] = todo.back();
-                todo.pop_back();
-                if (x < 0 || x >= n || y < 0 || y >= n || plane[x + (size_t)y * n] || !inside(x, y, extent)) continue;
-                plane[x + (size_t)y * n] = 1;
-                todo.emplace_back(x + 1, y); todo.emplace_back(x - 1, y); todo.emplace_back(x, y + 1); todo.emplace_back(x, y - 1);
+        obstacles_.assign((size_t)n * n * currentDepth_, 0);
+        if (!enableObstacle) { check(fs_set_obstacles(solver_, obstacles_.data(), (int64_t)obstacles_.size())); return; }
+        fs_obstacle_shape sh{};
+        sh.kind = (int)obstacleShape;
+        sh.center_x = obstaclePositionX * n; sh.center_y = obstaclePositionY * n; sh.center_z = obstaclePositionZ * currentDepth_;
+        sh.radius = obstacleRadius * n; sh.width = obstacleWidth * n; sh.height = obstacleHeight * n;
+        sh.depth = obstacleWidth * currentDepth_;
+        sh.seed_x = (int)std::nearbyint(obstaclePositionX * n); sh.seed_y = (int)std::nearbyint(obstaclePositionY * n);
+        sh.seed_z = currentDepth_ > 1 ? (int)std::nearbyint(obstaclePositionZ * currentDepth_) : 0;
+        check(fs_build_obstacles(solver_, &sh, &obstacleCells_));
+        check(fs_get_obstacles(solver_, obstacles_.data(), (int64_t)obstacles_.size()));
+    }
+    int64_t ObstacleCells() const { return obstacleCells_; }
+
+    // AddForceToArea, :452-483: velocity with linear fall-off, density inside 0.3 r -- ONE batched native call
+    void AddForceToArea(float centerX, float centerY, float forceX, float forceY, float radius) {
+        const int n = currentSize_;
+        auto clampi = [n](int v) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); };
+        std::vector<float> xs, ys, zs, ds, ax, ay;
+        for (int x = clampi((int)(centerX - radius)); x <= clampi((int)(centerX + radius)); x++)
+            for (int y = clampi((int)(centerY - radius)); y <= clampi((int)(centerY + radius)); y++) {
+                const float dx = (float)x - centerX, dy = (float)y - centerY;
+                const float distance = (float)std::sqrt((double)(dx * dx + dy * dy)); // Vector2.Distance
+                if (distance > radius) continue;
+                const float falloff = 1 - (distance / radius);
+                xs.push_back((float)x); ys.push_back((float)y); zs.push_back(sourcePositionZ * currentDepth_);
+                ax.push_back(forceX * falloff); ay.push_back(forceY * falloff);
+                ds.push_back(distance < radius * 0.3f ? sourceStrength * falloff : 0.0f);
+            }
+        if (xs.empty()) return;
+        check(fs_add_source_cells(solver_, (int64_t)xs.size(), xs.data(), ys.data(), zs.data(), ds.data(), ax.data(), ay.data(), nullptr));
+    }
+
+    // UpdateVisualization, :755-853: UpdateVisualizationJob on the device; returns currentSize^2 RGBA floats (Color[] layout)
+    fs_vis_params VisParams() const {
+        fs_vis_params v{};
+        const float white[4] = {1, 1, 1, 1}, blue[4] = {0, 0, 1, 1}, green[4] = {0, 1, 0, 1}, red[4] = {1, 0, 0, 1},
+                    gray[4] = {0.5f, 0.5f, 0.5f, 1}, yellow[4] = {1, 0.92156863f, 0.01568628f, 1};
+        auto set = [](float *d, const float *c) { for (int i = 0; i < 4; i++) d[i] = c[i]; };
+        v.color_mode = colorMode; v.visualize_source_position = visualizeSourcePosition; v.enable_custom_source = enableCustomSource;
+        v.source_x = sourcePositionX * currentSize_; v.source_y = sourcePositionY * currentSize_; v.visual_marker_radius = 3.0f; // :805-807
+        v.colour_intensity = colourIntensity;
+        v.medium_density_threshold = mediumDensityThreshold; v.high_density_threshold = highDensityThreshold;
+        v.low_pressure_threshold = lowPressureThreshold; v.high_pressure_threshold = highPressureThreshold;
+        set(v.fluid_color, white); set(v.obstacle_color, gray); set(v.source_position_color, yellow);
+        set(v.low_density_color, blue); set(v.medium_density_color, green); set(v.high_density_color, red);
+        set(v.low_pressure_color, blue); set(v.neutral_pressure_color, white); set(v.high_pressure_color, red);
+        v.gradient_key_count = 2; set(v.gradient_colors[0], blue); set(v.gradient_colors[1], red);           // Start(): :188-203
+        v.gradient_times[0] = 0.0f; v.gradient_times[1] = 1.0f;
+        v.z_slice = ViewSlice();
+        return v;
+    }
+    std::vector<float> UpdateVisualization() {
+        const fs_vis_params v = VisParams();
+        std::vector<float> rgba((size_t)currentSize_ * currentSize_ * 4);
+        check(fs_render_rgba(solver_, &v, rgba.data(), (int64_t)rgba.size()));
+        return rgba;
+    }
+
+    // DrawStreamlines, :886-959: the glyph jobs run on the device (fs_streamlines); Bresenham drawing (:1765-1849) here.
+    // Returns a currentSize^2 coverage mask (1 where streamlineColor is painted).
+    std::vector<uint8_t> DrawStreamlines() {
+        const int n = currentSize_;
+        const int skip = std::max(1, n / (streamlineDensity * 10));
+        const int64_t count = (int64_t)(n / skip) * (n / skip);
+        std::vector<float> seg((size_t)count * 4);
+        check(fs_streamlines(solver_, skip, streamlineScale, ViewSlice(), seg.data(), count));
+        std::vector<uint8_t> tex((size_t)n * n, 0);
+        const int halfThick = (int)std::floor(streamlineThickness / 2);
+        for (int64_t i = 0; i < count; i++) {
+            if (seg[4 * i] < 0) continue;
+            int x0 = (int)seg[4 * i], y0 = (int)seg[4 * i + 1], x1 = (int)std::nearbyint(seg[4 * i + 2]), y1 = (int)std::nearbyint(seg[4 * i + 3]);
+            const bool steep = std::abs(y1 - y0) > std::abs(x1 - x0);
+            if (steep) { std::swap(x0, y0); std::swap(x1, y1); }
+            if (x0 > x1) { std::swap(x0, x1); std::swap(y0, y1); }
+            const int dx = x1 - x0, dy = std::abs(y1 - y0), ystep = y0 < y1 ? 1 : -1;
+            int error = dx / 2, y = y0;
+            for (int x = x0; x <= x1; x++) {
+                for (int tx = -halfThick; tx <= halfThick; tx++)
+                    for (int ty = -halfThick; ty <= halfThick; ty++) {
+                        const int px = steep ? y + tx : x + tx, py = steep ? x + ty : y + ty;
+                        if (px >= 0 && px < n && py >= 0 && py < n) tex[px + (size_t)py * n] = 1;
+                    }
+                error -= dy;
+                if (error < 0) { y += ystep; error += dx; }
             }
         }
-        obstacles_.assign((size_t)n * n * currentDepth_, 0);
-        for (int k = 0; k < currentDepth_; k++) std::copy(plane.begin(), plane.end(), obstacles_.begin() + (size_t)k * n * n);
-        check(fs_set_obstacles(solver_, obstacles_.data(), (int64_t)obstacles_.size()));
+        return tex;
     }
 
     void AddDensity(float x, float y, float amount, float z = 0.0f) { check(fs_add_density(solver_, x, y, z, amount)); }       // :723
@@ -132,27 +215,16 @@ private:
     int currentSize_ = 0, currentDepth_ = 1;
     float cellSize_ = 0, dtScale_ = 1, elapsedTime_ = 0;
     std::vector<uint8_t> obstacles_;
+    int64_t obstacleCells_ = 0;
+    int ViewSlice() const {
+        if (currentDepth_ <= 1) return 0;
+        const int z = (int)std::nearbyint(viewSliceZ * currentDepth_);
+        return z < 0 ? 0 : (z > currentDepth_ - 1 ? currentDepth_ - 1 : z);
+    }
 
     static float clamp01(float v) { return v < 0 ? 0 : (v > 1 ? 1 : v); }
     void check(int rc) const {
         if (rc != FS_OK) throw std::runtime_error(std::string("fluidsolver: ") + fs_last_error(solver_));
-    }
-    bool inside(int x, int y, float extent) const { // IsInsideShape :353-388
-        const float cx = obstaclePositionX * currentSize_, cy = obstaclePositionY * currentSize_;
-        switch (obstacleShape) {
-        case ObstacleShape::Circle: return (x - cx) * (x - cx) + (y - cy) * (y - cy) < extent * extent;
-        case ObstacleShape::Rectangle: {
-            const float hw = obstacleWidth * currentSize_ * 0.5f, hh = obstacleHeight * currentSize_ * 0.5f;
-            return x > cx - hw && x < cx + hw && y > cy - hh && y < cy + hh;
-        }
-        default: {
-            const float chord = 2 * obstacleWidth * currentSize_, t = 0.15f;
-            const float u = (x - cx + chord / 2) / chord, v = (y - cy) / chord;
-            if (u < 0 || u > 1 || std::fabs(v) > t) return false;
-            const float half = 5 * t * (0.2969f * std::sqrt(u) - 0.1260f * u - 0.3516f * u * u + 0.2843f * u * u * u - 0.1015f * u * u * u * u);
-            return std::fabs(v) <= half;
-        }
-        }
     }
     // UpdateCustomSource, :485-533: the disc of AddDensity/AddVelocity calls as ONE batched native call
     void UpdateCustomSource() {

@@ -22,7 +22,12 @@ int main(int argc, char **argv) {
         sim.sourceRadius = 2.0f;
         sim.sourcePositionY = 0.2f;
         sim.ResetSimulation();
-        for (int f = 0; f < frames; f++) sim.Update();
+        if (argc > 4) sim.obstacleShape = (fluidsim::ObstacleShape)atoi(argv[4]);
+        sim.SetupObstacles();
+        for (int f = 0; f < frames; f++) {
+            sim.AddForceToArea(0.3f * size + f, 0.6f * size, 2.5f, -1.25f, 3.0f);
+            sim.Update();
+        }
         const fs_field fields[] = {FS_DENSITY, FS_VX, FS_VY, FS_PRESSURE};
         const char *names[] = {"density", "vx", "vy", "pressure"};
         for (int k = 0; k < 4; k++) {
@@ -34,6 +39,14 @@ int main(int argc, char **argv) {
         float mean, mx;
         sim.Metrics(&mean, &mx);
         printf("metrics %.9e %.9e\n", mean, mx);
+        sim.colorMode = 2; // DensityBased
+        const std::vector<float> rgba = sim.UpdateVisualization();
+        double csum = 0, csq = 0;
+        for (float v : rgba) { csum += v; csq += (double)v * v; }
+        printf("rgba %.9e %.9e\n", csum, csq);
+        long painted = 0;
+        for (uint8_t p : sim.DrawStreamlines()) painted += p;
+        printf("streamline_pixels %ld\n", painted);
         long obst = 0;
         for (uint8_t o : sim.Obstacles()) obst += o;
         printf("obstacle_cells %ld\n", obst);

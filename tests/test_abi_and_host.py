@@ -105,3 +105,62 @@ def test_update_order_matches_reference(pkg, emul_lib, oracle):
         got, want = sim.field(k), o.f[k]
         assert np.abs(got - want).max() <= 3e-6 * max(np.abs(want).max(), 1e-30), k
     sim.close()
+
+
+# ---- C# binding: struct layouts ---------------------------------------------------------------------------------
+def _c_struct_fields(name):
+    """[(field, array_suffix)] of a struct in include/fluidsolver.h, in declaration order."""
+    src = open(os.path.join(ROOT, "include", "fluidsolver.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1]
+        for n in names.split(","):
+            fields.append(re.match(r"\s*([a-z_0-9]+)", n.strip()).group(1))
+    return fields
+
+
+def _csharp_struct_layout(name):
+    """Sequential layout of a [StructLayout(Sequential)] struct of NativeFluidSolver.cs: [(field, offset)], size."""
+    src = open(os.path.join(ROOT, "Assets", "Plugin", "NativeFluidSolver.cs")).read()
+    body = re.search(r"public struct %s\s*\{(.*?)\n    \}" % name, src, re.S).group(1)
+    sizes = {"int": 4, "float": 4, "Color": 16}
+    out, off = [], 0
+    for line in body.splitlines():
+        line = line.split("//")[0].strip()
+        if "const" in line or not line.startswith(("public", "[MarshalAs")):
+            continue
+        m = re.match(r"(?:\[MarshalAs\(UnmanagedType\.ByValArray, SizeConst = (\d+)\)\]\s*)?public (\w+)(\[\])? ([\w, ]+);", line)
+        assert m, line
+        count, typ, names = int(m.group(1) or 1), m.group(2), [n.strip() for n in m.group(4).split(",")]
+        for n in names:
+            out.append((n, off))
+            off += sizes[typ] * count
+    declared = int(re.search(r"public const int NativeSize = (\d+);", body).group(1))
+    return out, off, declared
+
+
+@pytest.mark.parametrize("cname,csname", [("fs_params", "FsParams"), ("fs_vis_params", "FsVisParams"), ("fs_obstacle_shape", "FsObstacleShape")])
+def test_csharp_struct_layouts(tmp_path, cname, csname):
+    """The P/Invoke structs of Assets/Plugin/NativeFluidSolver.cs have the size and the field offsets of the C structs
+    they mirror (measured with a compiled C probe: sizeof / offsetof of every field of include/fluidsolver.h)."""
+    import subprocess
+
+    fields = _c_struct_fields(cname)
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "fluidsolver.h"\nint main(void){printf("%zu", sizeof(' + cname + '));'
+                     + "".join('printf(" %%zu", offsetof(%s, %s));' % (cname, f) for f in fields) + "return 0;}\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)], check=True)
+    nums = [int(v) for v in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    csize, coffs = nums[0], nums[1:]
+    cs, size, declared = _csharp_struct_layout(csname)
+    cs_offs = [o for _, o in cs]
+    if cname in ("fs_params", "fs_obstacle_shape"):   # `reserved[n]` is spelled as n scalar fields on the C# side
+        cs_offs = cs_offs[:len(coffs)]
+    assert size == csize == declared, (size, csize, declared)
+    assert cs_offs == coffs, list(zip(fields, coffs, cs))

@@ -8,6 +8,7 @@ CPU (host-emulated core behind the same C ABI) and GPU (libfluidsolver.so).
 * AddForceToArea (:452-483) through the host mirror against a cell-by-cell restatement applied to the oracle.
 """
 import importlib
+import os
 import math
 
 import numpy as np
@@ -189,3 +190,30 @@ def test_source_ring_many_calls_gpu(pkg, cuda_lib, oracle):
                 o.add_density(x, y, z, d); o.add_velocity(x, y, z, a, 0.0, 0.0)
         for name in ("density", "vx"):
             P.assert_exact(s.get_field(name), o.f[name], f"source ring {name}")
+
+
+# ---- persistence sink (N4, second half) -------------------------------------------------------------------------
+@pytest.mark.parametrize("jsonl", [False, True])
+def test_run_log_replaces_sql_cs(pkg, emul_lib, tmp_path, jsonl):
+    """SQL.SaveSimRunParams / LogRuntimeMetrics (SQL.cs:46-127) through the portable sink: one SimulationRuns row per
+    attached run with the reference's columns, one RuntimeMetrics row per step whose mean density / max speed are the
+    device reductions, and the reference's timeStep == 0.1f quirk on request."""
+    log = pkg.RunLog(str(tmp_path / ("runs.jsonl" if jsonl else "runs.db")), jsonl=jsonl)
+    sim = pkg.FluidSimulation(size=32, timeStep=0.05, lib_path=emul_lib, use_cuda_graph=False)
+    sim.enableCustomSource = True; sim.sourceEmitsVelocity = True; sim.sourcePositionY = 0.2   # outside the obstacle
+    run = sim.AttachRunLog(log)
+    assert run == 1
+    for _ in range(3):
+        sim.Update()
+    runs, metrics = log.rows("SimulationRuns"), log.rows("RuntimeMetrics")
+    assert len(runs) == 1 and runs[0]["Size"] == 32 and runs[0]["ObstacleType"] == "Circle" and abs(runs[0]["TimeStep"] - 0.05) < 1e-9
+    assert len(metrics) == 3 and all(m["RunID"] == 1 for m in metrics)
+    mean, mx = sim.metrics()
+    assert metrics[-1]["AverageDensity"] == pytest.approx(mean) and metrics[-1]["MaxVelocityMagnitude"] == pytest.approx(mx)
+    sim.close()
+    quirky = pkg.RunLog(str(tmp_path / "q.jsonl"), jsonl=True, reference_quirks=True)
+    sim = pkg.FluidSimulation(size=32, lib_path=emul_lib, use_cuda_graph=False)   # timeStep = 0.1f: SQL.cs:53-56 returns -1
+    assert sim.AttachRunLog(quirky) == -1
+    sim.Update()
+    assert not os.path.exists(str(tmp_path / "q.jsonl"))
+    sim.close(); log.close()
