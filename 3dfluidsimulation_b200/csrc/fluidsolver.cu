@@ -228,14 +228,28 @@ struct CudaExec {
     // ---- sweeps ----------------------------------------------------------------------------------
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
                const uint8_t *flags, float a, float c, int b, bool in_zero, bool fuse_halo) {
+        const float *ins[1] = {in}, *rhss[1] = {rhs}, *stales[1] = {stale};
+        float *outs[1] = {out};
+        relax_n(mode, g, 1, ins, rhss, stales, outs, flags, a, c, &b, in_zero, fuse_halo);
+    }
+    // One sweep over nf <= FS_BATCH fields that share a, c and the flags (the velocity components of a diffusion sweep),
+    // in ONE launch and, on z-slabs, ONE halo operation.
+    void relax_n(int mode, const FsGrid &g, int nf, const float *const *in, const float *const *rhs, const float *const *stale,
+                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, bool fuse_halo) {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
         const bool c_ok = c != 0.0f && c == c && c - c == 0.0f; // finite, non-zero: fs_div's precondition
         if (g.nx % 4 == 0 && !force_generic && c_ok) {
+            FsRelaxBatch batch{};
+            batch.nf = nf;
+            for (int f = 0; f < nf; f++) {
+                batch.in[f] = in[f]; batch.rhs[f] = rhs ? rhs[f] : nullptr; batch.stale[f] = stale ? stale[f] : nullptr;
+                batch.out[f] = out[f]; batch.b[f] = b[f];
+            }
             const int groups = g.nx / 4;
             // small grids: smaller CTAs so that there are enough of them to occupy 148 SMs
-            const long long thread_planes = (long long)groups * (g.ny - 2) * cnt;
+            const long long thread_planes = (long long)groups * (g.ny - 2) * cnt * nf;
             const int threads = thread_planes >= (long long)sm_count * 256 * 16 ? 256 : 64;
             int bx = 32;
             while (bx / 2 >= groups && bx > 1) bx /= 2;
@@ -245,7 +259,7 @@ struct CudaExec {
             // z chunk per CTA: short enough for >= ~4 waves of 4 resident CTAs/SM (tail effect), long enough
             // that re-reading the two halo planes per chunk stays <= 2/16 of one field
             const long long target = (long long)sm_count * 16;
-            long long zchunk = (long long)cnt * blocks_xy / target;
+            long long zchunk = (long long)cnt * blocks_xy * nf / target;
             if (zchunk < 4) zchunk = 4;
             if (zchunk > 16) zchunk = 16;
             if (tune_zchunk > 0) zchunk = tune_zchunk; // FS_ZCHUNK (experiments)
@@ -254,8 +268,8 @@ struct CudaExec {
             const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
             const dim3 block(bx, by, 1);
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
-    do { const dim3 grid(gxn, gyn, NZ_); \
-         relax_vec4<MODE_, HZ_><<<grid, block, 0, st>>>(g, in, rhs, stale, out, flags, a, c, b, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
+    do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
+         relax_vec4<MODE_, HZ_><<<grid, block, 0, st>>>(g, batch, flags, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
          launches++; } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
@@ -267,23 +281,28 @@ struct CudaExec {
                 { cudaStream_t main_st = st; st = st_halo;
                   FS_LAUNCH_RELAX_MODE(2, 0, nchunks - 1);     // the two chunks holding the slab's boundary planes
                   st = main_st; }
-                halo_on_stream(g, out, st_halo);               // stores them into the neighbours' ghosts, signals, awaits theirs
+                halo_n_on_stream(g, out, nf, st_halo);         // stores them into the neighbours' ghosts, signals, awaits theirs
                 FS_CUDA(cudaEventRecord(ev_join, st_halo));
                 FS_LAUNCH_RELAX_MODE(nchunks - 2, 1, 1);       // interior chunks, concurrently
                 FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join (also required before a graph capture ends)
             } else {
                 FS_LAUNCH_RELAX_MODE(nchunks, 0, 1);
-                if (halo_on && fuse_halo) halo(g, out);
+                if (halo_on && fuse_halo) halo_n_on_stream(g, out, nf, st);
             }
 #undef FS_LAUNCH_RELAX_MODE
 #undef FS_LAUNCH_RELAX
             return;
         }
-        if (mode == FS_MODE_SMOOTH)
-            cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
-        else
-            cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
-        if (fuse_halo) halo(g, out); // per-cell fallback: push after the whole sweep
+        for (int f = 0; f < nf; f++) {
+            const float *in_f = in[f], *rhs_f = rhs ? rhs[f] : nullptr, *stale_f = stale ? stale[f] : nullptr;
+            float *out_f = out[f];
+            const int b_f = b[f];
+            if (mode == FS_MODE_SMOOTH)
+                cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
+            else
+                cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
+        }
+        if (fuse_halo) halo_n_on_stream(g, out, nf, st); // per-cell fallback: push after the whole sweep
     }
     // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
@@ -370,6 +389,14 @@ struct CudaExec {
     }
     void mirror(const FsGrid &g, float *x, const uint8_t *flags, const long long *list, long long n, int b) {
         linear(n, [=] __device__(long long t) { fs_mirror_cell(g, x, flags, b, list[t]); });
+    }
+    // the obstacle pass on every velocity component in one launch (each component mirrors along its own axis)
+    void mirror3(const FsGrid &g, float *ux, float *uy, float *uz, const uint8_t *flags, const long long *list, long long n) {
+        const int nf = uz ? 3 : 2;
+        linear(n * nf, [=] __device__(long long t) {
+            const int f = (int)(t / n);
+            fs_mirror_cell(g, f == 0 ? ux : (f == 1 ? uy : uz), flags, f + 1, list[t - f * n]);
+        });
     }
     // launch geometry of the one-plane-per-thread float4 kernels
     bool vec4_geometry(const FsGrid &g, dim3 *grid, dim3 *block, int *kl0) {
@@ -680,19 +707,21 @@ struct CudaExec {
             if (bufs[i] == p) return (int)i;
         return -1;
     }
-    FsHaloArgs halo_args(const FsGrid &g, const float *field, unsigned op_offset) const {
+    FsHaloArgs halo_args(const FsGrid &g, float *const *fields, int nf, unsigned op_offset) const {
         FsHaloArgs h{};
         if (!halo_on) return h;
-        const int bi = field ? buf_index(field) : -1;
         h.my_flags = my_flags;
         h.op_offset = op_offset;
-        if (lo.present) {
-            h.lo_flags = lo.flags;
-            if (bi >= 0) h.lo_plane = lo.base[bi] + g.sz * (lo.nzl - FS_GHOST); // its FS_GHOST top ghost planes
-        }
-        if (hi.present) {
-            h.hi_flags = hi.flags;
-            if (bi >= 0) h.hi_plane = hi.base[bi];
+        h.nf = nf;
+        if (lo.present) h.lo_flags = lo.flags;
+        if (hi.present) h.hi_flags = hi.flags;
+        for (int f = 0; f < nf; f++) {
+            const int bi = buf_index(fields[f]);
+            // FS_GHOST planes each way: my lowest owned planes -> the lower neighbour's top ghosts, my highest -> the upper's bottom ghosts
+            h.lo_src[f] = fields[f] + g.sz * g.kb;
+            h.hi_src[f] = fields[f] + g.sz * (g.ke - FS_GHOST);
+            if (lo.present && bi >= 0) h.lo_plane[f] = lo.base[bi] + g.sz * (lo.nzl - FS_GHOST);
+            if (hi.present && bi >= 0) h.hi_plane[f] = hi.base[bi];
         }
         return h;
     }
@@ -700,18 +729,20 @@ struct CudaExec {
     // ordered after it can read the ghost planes without any further wait.
     void halo(const FsGrid &g, float *field) { halo_on_stream(g, field, st); }
     void halo_on_stream(const FsGrid &g, float *field, cudaStream_t stream) {
+        float *fields[1] = {field};
+        halo_n_on_stream(g, fields, field ? 1 : 0, stream);
+    }
+    void halo_n(const FsGrid &g, float *const *fields, int nf) { halo_n_on_stream(g, fields, nf, st); }
+    void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream) {
         if (!halo_on) return;
         const unsigned op = ++ops_since_commit;
-        const FsHaloArgs h = halo_args(g, field, op);
-        // FS_GHOST planes each way: my lowest owned planes -> the lower neighbour's top ghosts, my highest -> the upper's bottom ghosts
-        const float *lo_src = field ? field + g.sz * g.kb : nullptr, *hi_src = field ? field + g.sz * (g.ke - FS_GHOST) : nullptr;
+        const FsHaloArgs h = halo_args(g, fields, nf, op);
         const long long plane = g.sz * FS_GHOST;
-        int blocks = (int)((plane / 4 + 255) / 256);
+        int blocks = (int)((plane / 4 + 255) / 256) * (nf > 1 ? nf : 1);
         if (blocks > sm_count * 2) blocks = sm_count * 2;
-        if (blocks < 1 || !field) blocks = 1;
-        halo_push_kernel<<<blocks, 256, 0, stream>>>(h, lo_src, hi_src, field ? plane : 0);
+        if (blocks < 1 || nf == 0) blocks = 1;
+        halo_push_kernel<<<blocks, 256, 0, stream>>>(h, nf ? plane : 0);
         launches++;
-        (void)op; // the push kernel itself waits for the neighbours' planes of this op: nothing is left pending
     }
     void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
         if (!halo_on) return;

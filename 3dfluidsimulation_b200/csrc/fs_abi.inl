@@ -197,13 +197,7 @@ int fs_op_advect_velocity(fs_solver *s, float dt) {
     const float dt0 = dt * (float)(c.g.nx - 2);
     c.ex.halo_fence();
     c.ex.advect_velocity(c.g, c.vx, c.vy, c.vz, c.vx0, c.vy0, c.vz0, c.fl(), dt0);
-    if (c.g.hz && c.g_interior_obstacle) c.ex.halo(c.g, c.vz);
-    c.mirror(c.vx, 1);
-    c.mirror(c.vy, 2);
-    if (c.g.hz) c.mirror(c.vz, 3);
-    c.ex.halo(c.g, c.vx);
-    c.ex.halo(c.g, c.vy);
-    if (c.g.hz) c.ex.halo(c.g, c.vz);
+    c.finish_velocity(c.vx, c.vy, c.vz);
     return c.check();
 }
 
@@ -211,9 +205,8 @@ int fs_op_enforce_obstacles(fs_solver *s) {
     FS_GUARD(s);
     if (c.g_any_obstacle) {
         c.ex.enforce(c.g, c.vx, c.vy, c.vz, c.flags, c.prm.cell_size, c.prm.raw_viscosity);
-        c.ex.halo(c.g, c.vx);
-        c.ex.halo(c.g, c.vy);
-        if (c.g.hz) c.ex.halo(c.g, c.vz);
+        float *fields[3] = {c.vx, c.vy, c.vz};
+        c.ex.halo_n(c.g, fields, c.g.hz ? 3 : 2);
     }
     return c.check();
 }

@@ -92,6 +92,45 @@ FS_HD void fs_ring_scatter(const FsGrid &g, int i, int j, int kl, Emit emit) {
             for (int a = 0; a < nxs; a++) emit(xs[a], ys[bq], zs[c], fxs[a], fys[bq], fzs[c]);
 }
 
+// ---- obstacle mirroring fused into the sweeps -----------------------------------------------------------------
+// BoundaryJob's obstacle pass (:1261-1287) after a relaxation sweep sets an interior obstacle cell of a velocity field
+// (b = 1/2/3) to the mean of -x over its NON-obstacle neighbours along axis b, x being the values the sweep just wrote.
+// Those two values are recomputed here from the sweep's inputs (a non-obstacle interior neighbour n gets
+// (r[n] + a*nbsum(in, n))/c; a face cell of the ring gets set_bnd's value -v_self, v_self being the obstacle cell's own
+// pre-mirror value), so the thread that owns the obstacle cell can write the mirrored value in the same launch: no
+// separate mirror kernel and, on z-slabs, no extra halo round trip (the z neighbour of a boundary-plane cell lies in the
+// ghost zone, whose FS_GHOST = 2 planes hold everything the recomputation reads).
+template <int MODE>
+FS_HD float fs_relax_new(const FsGrid &g, const float *in, const float *rhs, float a, float c, bool in_zero, long long n) {
+    float s, r;
+    if (in_zero) {
+        s = ((0.0f + 0.0f) + 0.0f) + 0.0f;
+        if (g.hz) s = (s + 0.0f) + 0.0f;
+        r = rhs[n];
+    } else {
+        s = ((in[n + 1] + in[n - 1]) + in[n + g.sy]) + in[n - g.sy];
+        if (g.hz) s = (s + in[n + g.sz]) + in[n - g.sz];
+        r = MODE == FS_MODE_JACOBI ? rhs[n] : in[n];
+    }
+    return (r + a * s) / c;
+}
+// f: the cell's obstacle flag byte; v_self: its pre-mirror value (what the ring cells next to it are derived from).
+template <int MODE>
+FS_HD float fs_mirror_fused(const FsGrid &g, const float *in, const float *rhs, uint8_t f, float a, float c, int b,
+                            bool in_zero, float v_self, int i, int j, int kl) {
+    const long long idx = fs_idx(g, i, j, kl);
+    const long long step = b == 1 ? 1 : (b == 2 ? g.sy : g.sz);
+    const uint8_t lo = b == 1 ? FS_OB_XM : (b == 2 ? FS_OB_YM : FS_OB_ZM);
+    const uint8_t hi = b == 1 ? FS_OB_XP : (b == 2 ? FS_OB_YP : FS_OB_ZP);
+    const int pos = b == 1 ? i : (b == 2 ? j : kl + g.zoff), last = b == 1 ? g.nx - 1 : (b == 2 ? g.ny - 1 : g.nz - 1);
+    float m = 0.0f;
+    int count = 0;
+    if (!(f & lo)) { m += -(pos - 1 == 0 ? -v_self : fs_relax_new<MODE>(g, in, rhs, a, c, in_zero, idx - step)); count++; }
+    if (!(f & hi)) { m += -(pos + 1 == last ? -v_self : fs_relax_new<MODE>(g, in, rhs, a, c, in_zero, idx + step)); count++; }
+    return count > 0 ? m / (float)count : 0.0f;
+}
+FS_HD bool fs_mirrors(const FsGrid &g, int b) { return b != 0 && (b != 3 || g.hz); }
+
 // ---- relaxation sweeps ---------------------------------------------------------------------------
 // MODE SMOOTH: DiffuseJob :1045-1068  out = (in[c] + a*nbsum(in))/c, obstacle cells keep the stale
 //              content of the output buffer (`stale`: x0 during the first two iterations because both
@@ -131,6 +170,9 @@ FS_HD void fs_relax_cell(const FsGrid &g, const float *in, const float *rhs, con
         if (fx | fy | fz) out[fs_idx(g, ii, jj, kk)] = fs_ring_value(v, fx, fy, fz, b);
         else if (write_self) out[idx] = v;
     });
+    // the obstacle pass of BoundaryJob, fused (the ring cells above were derived from the pre-mirror value, as in the
+    // reference's order faces -> corners -> obstacles)
+    if (obst && fs_mirrors(g, b)) out[idx] = fs_mirror_fused<MODE>(g, in, rhs, flags[idx], a, c, b, in_zero, v, i, j, kl);
 }
 
 // Red-black half sweep (colour = (i+j+k)&1 with GLOBAL k), in place, no ring writes; set_bnd is a

@@ -212,19 +212,12 @@ struct SolverCore {
     void mirror(float *x, int b) {
         if (b != 0 && n_obst && (b != 3 || g.hz)) ex.mirror(g, x, flags, obst_list, n_obst, b);
     }
-    // One relaxation sweep + its boundary work.  Single slab: sweep, obstacle mirroring.  Several slabs: the
-    // executor overlaps the push of the boundary planes with the interior of the same sweep (fuse_halo) unless obstacle
-    // mirroring has to run on the boundary planes first (b != 0 with obstacles): then the order is
-    // sweep, [halo when the mirror reads z neighbours], mirror, halo.
+    // One relaxation sweep with all of BoundaryJob fused into it: the set_bnd ring (ring scatter) and, for velocity
+    // components, the obstacle mirroring (fs_mirror_fused recomputes the two neighbour values it needs).  On z-slabs the
+    // executor overlaps the push of the boundary planes with the interior of the same sweep.
     void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,
                   bool in_zero) {
-        const bool mir = needs_mirror(b); // global decision, see g_interior_obstacle
-        ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/!mir);
-        if (mir) {
-            if (b == 3) ex.halo(g, out);
-            mirror(out, b);
-            ex.halo(g, out);
-        }
+        ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/true);
     }
     // Whether sweeps of field kind b may be fused in pairs: no obstacle mirroring between the two stages.
     bool needs_mirror(int b) const { return b != 0 && g_interior_obstacle && (b != 3 || g.hz); }
@@ -304,6 +297,45 @@ struct SolverCore {
             if (b != 0) ex.halo(g, x);
         }
     }
+    // ---- batched Diffuse of the velocity components (VelocityStep :705-706 + the z component) ---------------------------
+    // The components share a, c and the obstacle flags and are independent until the projection, so each of their 2*K_d
+    // sweeps is ONE launch over all of them (and one halo operation on z-slabs) instead of one per component.  Ping-pong
+    // partners: tmp, pressure and div, all dead at this point of the step (ProjectWithJobs rewrites the latter two).
+    void diffuse_velocity(float visc, float dt) {
+        float a, c;
+        coeffs(g.nx, visc, dt, &a, &c);
+        const int nf = g.hz ? 3 : 2, iters = prm.iters_diffuse;
+        if (pair_ok(1, c, FS_PAIR_SMOOTH) || iters == 0) { // fused pairs are issued per field
+            diffuse(1, vx0, vx, visc, dt);
+            diffuse(2, vy0, vy, visc, dt);
+            if (g.hz) diffuse(3, vz0, vz, visc, dt);
+            return;
+        }
+        const int b[3] = {1, 2, 3};
+        float **x[3] = {&vx0, &vy0, &vz0}, **scratch[3] = {&tmp, &pressure, &div};
+        const float *x0[3] = {vx, vy, vz};
+        // pass 1 (DiffuseWithJobs): x0 -> scratch -> x -> ...
+        const float *in[3] = {x0[0], x0[1], x0[2]}, *stale[3];
+        float *out[3], *A[3], *B[3];
+        for (int f = 0; f < nf; f++) { A[f] = *scratch[f]; B[f] = *x[f]; }
+        for (int it = 0; it < iters; it++) {
+            for (int f = 0; f < nf; f++) {
+                out[f] = (it & 1) ? B[f] : A[f];
+                stale[f] = (!needs_mirror(b[f]) || it < 2) ? x0[f] : nullptr; // see smooth()
+            }
+            ex.relax_n(FS_MODE_SMOOTH, g, nf, in, nullptr, stale, out, fl(), a, c, b, false, true);
+            for (int f = 0; f < nf; f++) in[f] = out[f];
+        }
+        // pass 2 (LinearSolveWithJobs) seeded with pass 1's result, rhs = x0
+        float *rd[3], *wr[3];
+        for (int f = 0; f < nf; f++) { rd[f] = const_cast<float *>(in[f]); wr[f] = rd[f] == A[f] ? B[f] : A[f]; }
+        for (int it = 0; it < iters; it++) {
+            const float *rdc[3] = {rd[0], rd[1], rd[2]};
+            ex.relax_n(FS_MODE_JACOBI, g, nf, rdc, x0, nullptr, wr, fl(), a, c, b, false, true);
+            for (int f = 0; f < nf; f++) std::swap(rd[f], wr[f]);
+        }
+        for (int f = 0; f < nf; f++) { *x[f] = rd[f]; *scratch[f] = wr[f]; }
+    }
     void diffuse(int b, float *&x, const float *x0, float diff, float dt) {
         float a, c;
         coeffs(g.nx, diff, dt, &a, &c);
@@ -322,32 +354,25 @@ struct SolverCore {
         else
             lin_solve(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true); // :1581-1582, p starts 0
         ex.gradient(g, ux, uy, uz, pressure, fl());
+        finish_velocity(ux, uy, uz);
+    }
+    // BoundaryJob's obstacle pass on all velocity components (one launch) and their halos (one operation).
+    void finish_velocity(float *ux, float *uy, float *uz) {
         if (g.hz && g_interior_obstacle) ex.halo(g, uz); // slabs: the z mirror reads the neighbours' new boundary planes
-        mirror(ux, 1);
-        mirror(uy, 2);
-        if (g.hz) mirror(uz, 3);
-        ex.halo(g, ux);
-        ex.halo(g, uy);
-        if (g.hz) ex.halo(g, uz);
+        if (n_obst) ex.mirror3(g, ux, uy, g.hz ? uz : nullptr, flags, obst_list, n_obst);
+        float *fields[3] = {ux, uy, uz};
+        ex.halo_n(g, fields, g.hz ? 3 : 2);
     }
 
     // ---- the step (Simulate, FluidSim.cs:551-570) -----------------------------------------------
     void step_body(float dt, float visc, float diff) {
         const float dt0 = dt * (float)(g.nx - 2); // :1526
         // VelocityStep :703-714
-        diffuse(1, vx0, vx, visc, dt);
-        diffuse(2, vy0, vy, visc, dt);
-        if (g.hz) diffuse(3, vz0, vz, visc, dt);
+        diffuse_velocity(visc, dt);
         project(vx0, vy0, vz0);
         ex.halo_fence(); // slabs: the back-trace may gather from a neighbour slab, whose fields must be complete
         ex.advect_velocity(g, vx, vy, vz, vx0, vy0, vz0, fl(), dt0); // :710-711
-        if (g.hz && g_interior_obstacle) ex.halo(g, vz);
-        mirror(vx, 1);
-        mirror(vy, 2);
-        if (g.hz) mirror(vz, 3);
-        ex.halo(g, vx);
-        ex.halo(g, vy);
-        if (g.hz) ex.halo(g, vz);
+        finish_velocity(vx, vy, vz);
         project(vx, vy, vz);
         // DensityStep :716-721
         diffuse(0, dens0, density, diff, dt);
@@ -356,9 +381,8 @@ struct SolverCore {
         ex.halo(g, density);
         if (prm.enable_obstacle && g_any_obstacle) { // :567-570 (global decision; the kernel is a no-op where flags are 0)
             ex.enforce(g, vx, vy, vz, flags, prm.cell_size, prm.raw_viscosity);
-            ex.halo(g, vx);
-            ex.halo(g, vy);
-            if (g.hz) ex.halo(g, vz);
+            float *fields[3] = {vx, vy, vz};
+            ex.halo_n(g, fields, g.hz ? 3 : 2);
         }
         ex.halo_commit();
     }

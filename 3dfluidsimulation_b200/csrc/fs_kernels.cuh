@@ -137,11 +137,15 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 // pressure / lost uniform registers, see profiles/r01d_halo_variants.md, so the sweep kernel stays untouched.)
 enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_CNT_HI = 4, FS_HF_ERROR = 5, FS_HF_WORDS = 8 };
 
+#define FS_BATCH 3 // fields per batched launch / halo operation (the velocity components)
 struct FsHaloArgs {
-    float *lo_plane;        // lower neighbour's top ghost plane of the output field (nullptr: no neighbour)
-    float *hi_plane;        // upper neighbour's plane 0 of the output field
-    unsigned *my_flags;     // this slab's flag block
-    unsigned *lo_flags;     // neighbours' flag blocks (peer memory)
+    float *lo_plane[FS_BATCH];       // lower neighbour's top ghost planes of each field (nullptr: no neighbour / fence)
+    float *hi_plane[FS_BATCH];       // upper neighbour's bottom ghost planes
+    const float *lo_src[FS_BATCH];   // this slab's lowest / highest owned planes of each field
+    const float *hi_src[FS_BATCH];
+    int nf;                          // number of fields (0: pure fence)
+    unsigned *my_flags;              // this slab's flag block
+    unsigned *lo_flags;              // neighbours' flag blocks (peer memory)
     unsigned *hi_flags;
     unsigned op_offset;
 };
@@ -180,10 +184,10 @@ __device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
     return *(volatile const unsigned *)(h.my_flags + FS_HF_BASE) + h.op_offset;
 }
 
-// Standalone form for the once-per-step kernels: copies the two boundary planes of `field` (nullptr: pure
-// fence) after waiting for seq-1, then signals seq.  plane_elems = nx*ny.
+// Copies the FS_GHOST boundary planes of up to FS_BATCH fields into the neighbours' ghost planes (nf = 0: pure fence)
+// after waiting for seq-1, then signals seq and waits for the neighbours' seq.  plane_elems = FS_GHOST*nx*ny.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const float *__restrict__ hi_src, long long plane_elems) {
+halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) {
         const unsigned seq = halo_seq(h);
@@ -193,13 +197,19 @@ halo_push_kernel(const FsHaloArgs h, const float *__restrict__ lo_src, const flo
     }
     __syncthreads();
     const long long n4 = plane_elems / 4, stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
-        if (h.lo_plane && lo_src) reinterpret_cast<float4 *>(h.lo_plane)[t] = reinterpret_cast<const float4 *>(lo_src)[t];
-        if (h.hi_plane && hi_src) reinterpret_cast<float4 *>(h.hi_plane)[t] = reinterpret_cast<const float4 *>(hi_src)[t];
-    }
-    for (long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane_elems; t += stride) {
-        if (h.lo_plane && lo_src) h.lo_plane[t] = lo_src[t];
-        if (h.hi_plane && hi_src) h.hi_plane[t] = hi_src[t];
+#pragma unroll
+    for (int f = 0; f < FS_BATCH; f++) {
+        if (f >= h.nf) break;
+        float *lo_dst = h.lo_plane[f], *hi_dst = h.hi_plane[f];
+        const float *lo_src = h.lo_src[f], *hi_src = h.hi_src[f];
+        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+            if (lo_dst) reinterpret_cast<float4 *>(lo_dst)[t] = reinterpret_cast<const float4 *>(lo_src)[t];
+            if (hi_dst) reinterpret_cast<float4 *>(hi_dst)[t] = reinterpret_cast<const float4 *>(hi_src)[t];
+        }
+        for (long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane_elems; t += stride) {
+            if (lo_dst) lo_dst[t] = lo_src[t];
+            if (hi_dst) hi_dst[t] = hi_src[t];
+        }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -246,12 +256,26 @@ __device__ __forceinline__ const float *fs_slab_plane(const FsSlabView &v, const
 // 512^3).  A register prefetch of the next plane was measured and rejected (78 registers -> 3 CTAs/SM, 336 us).
 // Grid: x = ceil(nx/4 / blockDim.x), y = ceil((ny-2) / blockDim.y), z = number of z chunks.
 // kl_begin/kl_end: owned interior local planes [kl_begin, kl_end); each block marches zchunk of them.
+// Up to FS_BATCH fields per launch (the velocity components of one diffusion sweep share a, c and the flags): blockIdx.z
+// enumerates (z chunk, field), each CTA works on one field, so batching costs the inner loop nothing.
+struct FsRelaxBatch {
+    const float *in[FS_BATCH], *rhs[FS_BATCH], *stale[FS_BATCH];
+    float *out[FS_BATCH];
+    int b[FS_BATCH];
+    int nf;
+};
 template <int MODE, bool HZ>
 __global__ void __launch_bounds__(256, 4)
-relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict__ rhs, const float *stale,
-           float *out, const uint8_t *__restrict__ flags, const float a, const float c, const int b,
+relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const float a, const float c,
            const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
            const int zc_stride, const int l2_ahead) {
+    const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
+    const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
+    const float *__restrict__ in = fld == 0 ? batch.in[0] : (fld == 1 ? batch.in[1] : batch.in[2]);
+    const float *__restrict__ rhs = fld == 0 ? batch.rhs[0] : (fld == 1 ? batch.rhs[1] : batch.rhs[2]);
+    const float *stale = fld == 0 ? batch.stale[0] : (fld == 1 ? batch.stale[1] : batch.stale[2]);
+    float *out = fld == 0 ? batch.out[0] : (fld == 1 ? batch.out[1] : batch.out[2]);
+    const int b = fld == 0 ? batch.b[0] : (fld == 1 ? batch.b[1] : batch.b[2]);
     const int gx = blockIdx.x * blockDim.x + threadIdx.x;
     const int x0 = gx * 4;
     const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
@@ -259,7 +283,7 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
     // sweep is issued as two launches of this same kernel -- the two chunks that hold the slab's boundary planes
     // first (base 0, stride nchunks-1), then the interior chunks (base 1, stride 1) -- with the P2P halo push
     // between them, so the exchange overlaps the interior (fluidsolver.cu, CudaExec::relax).
-    const int zc = zc_base + (int)blockIdx.z * zc_stride;
+    const int zc = zc_base + zblk * zc_stride;
     const int k_lo = kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
@@ -353,6 +377,18 @@ relax_vec4(const FsGrid g, const float *__restrict__ in, const float *__restrict
 #pragma unroll
                     for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
                     st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+                }
+            }
+        }
+        // BoundaryJob's obstacle pass, fused: a velocity component's obstacle cells take the mirrored mean of their
+        // fluid neighbours' NEW values along axis b (recomputed, see fs_mirror_fused); the stores above wrote the
+        // pre-mirror value, this thread's later store wins
+        if ((fl & 0x01010101u) && b != 0) {
+            if (b != 3 || HZ) {
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    if (!((fl >> (8 * l)) & 1u) || (l == 0 && first_x) || (l == 3 && last_x)) continue;
+                    pout[l] = fs_mirror_fused<MODE>(g, in, rhs, (uint8_t)(fl >> (8 * l)), a, c, b, in_zero != 0, v[l], x0 + l, j, kl);
                 }
             }
         }

@@ -64,6 +64,15 @@ struct HostExec {
             cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         if (fuse_halo) halo(g, out);
     }
+    void relax_n(int mode, const FsGrid &g, int nf, const float *const *in, const float *const *rhs, const float *const *stale,
+                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, bool fuse_halo) {
+        for (int f = 0; f < nf; f++)
+            relax(mode, g, in[f], rhs ? rhs[f] : nullptr, stale ? stale[f] : nullptr, out[f], flags, a, c, b[f], in_zero, false);
+        if (fuse_halo) halo_n(g, out, nf);
+    }
+    void halo_n(const FsGrid &g, float *const *fields, int nf) {
+        for (int f = 0; f < nf; f++) halo(g, fields[f]);
+    }
     // Fused two-stage sweep, emulated with the per-cell functions and LOCAL data only (so that the CPU tier checks the
     // two-plane halo logic): stage 1 on the owned interior planes plus one plane each side into a scratch copy of
     // `in`, stage 2 on the owned interior planes.  FS_EMUL_NO_PAIR=1 makes the orchestration fall back to single sweeps.
@@ -131,6 +140,11 @@ struct HostExec {
     void mirror(const FsGrid &g, float *x, const uint8_t *flags, const long long *list, long long n, int b) {
         for (long long t = n - 1; t >= 0; t--) fs_mirror_cell(g, x, flags, b, list[t]);
         launches++;
+    }
+    void mirror3(const FsGrid &g, float *ux, float *uy, float *uz, const uint8_t *flags, const long long *list, long long n) {
+        mirror(g, ux, flags, list, n, 1);
+        mirror(g, uy, flags, list, n, 2);
+        if (uz) mirror(g, uz, flags, list, n, 3);
     }
     void divergence(const FsGrid &g, float *div, const float *ux, const float *uy, const float *uz) {
         cells(g, [&](int i, int j, int kl) { fs_divergence_cell(g, div, ux, uy, uz, i, j, kl); });
