@@ -40,6 +40,7 @@ struct CudaExec {
     int pair_rows = FS_PAIR_MAX_ROWS, pair_zchunk = 0; // FS_PAIR_ROWS / FS_PAIR_ZCHUNK (experiments)
     int pair_mode = 2;          // FS_PAIR: 0 never use the fused two-stage sweep, 1 always, 2 auto (see pair_supported)
     bool pair_force = false;
+    bool no_advect_vec4 = false; // FS_NO_ADVECT_VEC4=1: per-cell advect kernels (tests compare both)
     bool pair_slabs = true;     // FS_PAIR_SLABS=0: auto mode does not fuse Jacobi / smoother sweeps on z-slabs
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
@@ -104,6 +105,7 @@ struct CudaExec {
         if (const char *e = getenv("FS_BLOCK_Y")) tune_by = atoi(e);
         if (const char *e = getenv("FS_PAIR_ROWS")) pair_rows = atoi(e);
         if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
+        if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -447,6 +449,16 @@ struct CudaExec {
     void advect(const FsGrid &g, float *d, const float *d0, const float *ux, const float *uy, const float *uz,
                 const uint8_t *flags, float dt0, int b) {
         const FsSlabView v = slab_view(g, d0);
+        dim3 grid, block;
+        int kl0;
+        if (!no_advect_vec4 && vec4_geometry(g, &grid, &block, &kl0)) {
+            FsAdvectBatch ab{};
+            ab.dst[0] = d; ab.src[0] = v; ab.b[0] = b;
+            if (g.hz) advect_vec4<1, true><<<grid, block, 0, st>>>(g, ab, ux, uy, uz, flags, dt0, kl0);
+            else advect_vec4<1, false><<<grid, block, 0, st>>>(g, ab, ux, uy, uz, flags, dt0, kl0);
+            launches++;
+            return;
+        }
         cells(g, [=] __device__(int i, int j, int kl) {
             auto samp = [&](int kk) { return fs_slab_plane(v, g, kk); };
             fs_advect_cell(g, d, samp, ux, uy, uz, flags, dt0, b, i, j, kl);
@@ -455,6 +467,18 @@ struct CudaExec {
     void advect_velocity(const FsGrid &g, float *dx, float *dy, float *dz, const float *sx, const float *sy,
                          const float *sz, const uint8_t *flags, float dt0) {
         const FsSlabView vx_ = slab_view(g, sx), vy_ = slab_view(g, sy), vz_ = g.hz ? slab_view(g, sz) : FsSlabView{};
+        dim3 grid, block;
+        int kl0;
+        if (!no_advect_vec4 && vec4_geometry(g, &grid, &block, &kl0)) {
+            FsAdvectBatch ab{};
+            ab.dst[0] = dx; ab.dst[1] = dy; ab.dst[2] = dz;
+            ab.src[0] = vx_; ab.src[1] = vy_; ab.src[2] = vz_;
+            ab.b[0] = 1; ab.b[1] = 2; ab.b[2] = 3;
+            if (g.hz) advect_vec4<3, true><<<grid, block, 0, st>>>(g, ab, sx, sy, sz, flags, dt0, kl0);
+            else advect_vec4<2, false><<<grid, block, 0, st>>>(g, ab, sx, sy, sz, flags, dt0, kl0);
+            launches++;
+            return;
+        }
         cells(g, [=] __device__(int i, int j, int kl) {
             auto px = [&](int kk) { return fs_slab_plane(vx_, g, kk); };
             auto py = [&](int kk) { return fs_slab_plane(vy_, g, kk); };

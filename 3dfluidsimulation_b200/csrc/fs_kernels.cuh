@@ -687,6 +687,88 @@ gradient_vec4(const FsGrid g, float *vx, float *vy, float *vz, const float *__re
     }
 }
 
+// AdvectJob :1138-1185 + BoundaryJob, float4 per thread, NF fields along one shared back-trace (NF = 3: the velocity
+// components of VelocityStep :710-711; NF = 1: density or a single component).  The per-cell form issues 8 scalar gathers
+// per cell and field (24 + 3 loads per cell for the velocity) and is bound by load-instruction / L1 wavefront throughput
+// (1.3 TB/s at 512^3).  Here a thread owns 4 consecutive cells; wherever they share one integer displacement
+// (i0 - i, j0, k0 equal, i0 - i in {-1, 0}: everywhere the flow moves less than a cell per step, i.e. the whole grid
+// outside the plume core) the 5 source values a row contributes come from ONE 16-byte load plus one scalar, 8 loads per
+// field for 4 cells instead of 32.  Other threads fall back to the per-cell gathers.  Same arithmetic, bit for bit.
+struct FsAdvectBatch {
+    float *dst[FS_BATCH];
+    FsSlabView src[FS_BATCH];
+    int b[FS_BATCH];
+};
+__device__ __forceinline__ void fs_row5(const float *row, int x0, int di, bool first_x, bool last_x, float r[5]) {
+    const float4 m = ld4(row + x0);                      // cells x0 .. x0+3
+    if (di == 0) {
+        r[0] = m.x; r[1] = m.y; r[2] = m.z; r[3] = m.w;
+        r[4] = last_x ? 0.0f : __ldg(row + x0 + 4);       // only the ring lane of the last float4 would use it
+    } else {
+        r[1] = m.x; r[2] = m.y; r[3] = m.z; r[4] = m.w;
+        r[0] = first_x ? 0.0f : __ldg(row + x0 - 1);
+    }
+}
+template <int NF, bool HZ>
+__global__ void __launch_bounds__(256)
+advect_vec4(const FsGrid g, const FsAdvectBatch ab, const float *__restrict__ velx, const float *__restrict__ vely,
+            const float *__restrict__ velz, const uint8_t *__restrict__ flags, const float dt0, const int kl0) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int j = 1 + blockIdx.y * blockDim.y + threadIdx.y;
+    const int kl = kl0 + blockIdx.z;
+    if (x0 >= g.nx || j > g.ny - 2) return;
+    const FsVec4Pos pos = fs_vec4_pos(g, x0, j, kl);
+    const long long idx = fs_idx(g, x0, j, kl);
+    const float4 ux = ld4(velx + idx), uy = ld4(vely + idx);
+    float4 uz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (HZ) uz = ld4(velz + idx);
+    const uint32_t fl = flags ? ld_flags4(flags + idx) : 0u;
+    const float uxv[4] = {ux.x, ux.y, ux.z, ux.w}, uyv[4] = {uy.x, uy.y, uy.z, uy.w}, uzv[4] = {uz.x, uz.y, uz.z, uz.w};
+    FsAdvectWeights w[4];
+#pragma unroll
+    for (int l = 0; l < 4; l++) w[l] = fs_advect_weights(g, dt0, uxv[l], uyv[l], uzv[l], x0 + l, j, kl + g.zoff);
+    const int di = w[0].i0 - x0;
+    bool uniform = di == 0 || di == -1;
+#pragma unroll
+    for (int l = 1; l < 4; l++) uniform = uniform && (w[l].i0 - (x0 + l) == di) && w[l].j0 == w[0].j0 && w[l].k0 == w[0].k0;
+#pragma unroll
+    for (int f = 0; f < NF; f++) {
+        const FsSlabView &sv = ab.src[f];
+        float v[4];
+        if (uniform) {
+            const float *p0 = fs_slab_plane(sv, g, w[0].k0) + w[0].j0 * g.sy;
+            float A[5], B[5];
+            fs_row5(p0, x0, di, pos.first_x, pos.last_x, A);
+            fs_row5(p0 + g.sy, x0, di, pos.first_x, pos.last_x, B);
+            float lo[4];
+#pragma unroll
+            for (int l = 0; l < 4; l++)
+                lo[l] = w[l].s0 * (w[l].t0 * A[l] + w[l].t1 * B[l]) + w[l].s1 * (w[l].t0 * A[l + 1] + w[l].t1 * B[l + 1]);
+            if (HZ) {
+                const float *p1 = fs_slab_plane(sv, g, w[0].k0 + 1) + w[0].j0 * g.sy;
+                float C[5], D[5];
+                fs_row5(p1, x0, di, pos.first_x, pos.last_x, C);
+                fs_row5(p1 + g.sy, x0, di, pos.first_x, pos.last_x, D);
+#pragma unroll
+                for (int l = 0; l < 4; l++) {
+                    const float hi = w[l].s0 * (w[l].t0 * C[l] + w[l].t1 * D[l]) + w[l].s1 * (w[l].t0 * C[l + 1] + w[l].t1 * D[l + 1]);
+                    v[l] = w[l].u0 * lo[l] + w[l].u1 * hi;
+                }
+            } else {
+#pragma unroll
+                for (int l = 0; l < 4; l++) v[l] = lo[l];
+            }
+        } else {
+#pragma unroll
+            for (int l = 0; l < 4; l++) v[l] = fs_advect_interp(g, w[l], [&](int kk) { return fs_slab_plane(sv, g, kk); });
+        }
+#pragma unroll
+        for (int l = 0; l < 4; l++)
+            if ((fl >> (8 * l)) & 1u) v[l] = 0.0f;      // the reference's output array is fresh: obstacle cells get 0 (:1529, :1148-1156)
+        fs_vec4_store_ring(ab.dst[f], g, pos, v, ab.b[f]);
+    }
+}
+
 // Red-black Gauss-Seidel half sweep (BASELINE config 5; oracle fo_lin_solve_rb), float4 per thread, in place.
 // A cell of colour (i+j+k)&1 reads only cells of the other colour, which no thread writes in this launch, so
 // the update order is free.  The colour-1 launch also performs set_bnd (ring scatter from the now final row),

@@ -117,12 +117,21 @@ def case_project(lib, O, nx, ny, nz, seed=3, obstacles=True, iters=7):
             assert_exact(s.get_field(n), w, f"project {n} {shape}")
 
 
-def case_advect(lib, O, nx, ny, nz, seed=4, obstacles=True, vscale=3.0):
+def case_advect(lib, O, nx, ny, nz, seed=4, obstacles=True, vscale=3.0, coherent=False):
+    """coherent=True: sub-cell displacements whose sign is constant over large blocks (plus a block of exact zeros), the
+    regime of a real flow away from the plume core -- what the float4 kernel's shared-displacement path handles."""
     rng = np.random.default_rng(seed)
     shape = shape_of(nx, ny, nz)
     mask = random_mask(shape, rng) if obstacles else np.zeros(shape, np.uint8)
     d0 = rnd(shape, rng)
     v = [rnd(shape, rng, vscale) for _ in range(3)]
+    if coherent:
+        for n, a in enumerate(v):
+            a[...] = np.abs(a) * f32(0.2 / (0.05 * max(nx - 2, 1)) / max(vscale, 1e-6))   # |displacement| < 0.2 cells
+            sl = [slice(None)] * a.ndim
+            sl[n % a.ndim] = slice(a.shape[n % a.ndim] // 2, None)
+            a[tuple(sl)] *= f32(-1)                                                          # sign flips half way along one axis
+            a[tuple(slice(0, max(1, d // 3)) for d in a.shape)] = 0                          # a corner block at rest
     vz = v[2] if nz > 1 else None
     dt = 0.05
     with make_solver(lib, nx, ny, nz) as s:

@@ -164,3 +164,18 @@ def test_csharp_struct_layouts(tmp_path, cname, csname):
         cs_offs = cs_offs[:len(coffs)]
     assert size == csize == declared, (size, csize, declared)
     assert cs_offs == coffs, list(zip(fields, coffs, cs))
+
+
+def test_csharp_binds_every_entry_point():
+    """One [DllImport] per function of include/fluidsolver.h in Assets/Plugin/NativeFluidSolver.cs (the P/Invoke layer the
+    Unity scene loads), and the component uses the entry points of the frame path."""
+    cs = open(os.path.join(ROOT, "Assets", "Plugin", "NativeFluidSolver.cs")).read()
+    bound = set(re.findall(r"public static extern \w+ (fs_[a-z_0-9]+)\(", cs))
+    assert sorted(bound) == declared_functions()
+    comp = open(os.path.join(ROOT, "Assets", "Plugin", "FluidSimulationNative.cs")).read()
+    for name in ("fs_create", "fs_build_obstacles", "fs_add_source_cells", "fs_step", "fs_render_rgba", "fs_streamlines",
+                 "fs_get_metrics", "fs_add_density", "fs_add_velocity"):
+        assert "Native." + name in comp, name
+    for method in ("AddForceToArea", "UpdateVisualization", "DrawStreamlines", "SetupObstacles", "SetPaused", "GetSourcePosition",
+                   "SetSourcePosition", "SaveCurrentConfiguration"):
+        assert re.search(r"\b%s\(" % method, comp), method

@@ -41,8 +41,35 @@ def test_project(lib, oracle, dims):
 
 
 @pytest.mark.parametrize("dims", GRIDS)
-def test_advect(lib, oracle, dims):
-    P.case_advect(lib, oracle, *dims)
+@pytest.mark.parametrize("coherent", [False, True])
+def test_advect(lib, oracle, dims, coherent):
+    P.case_advect(lib, oracle, *dims, coherent=coherent)
+
+
+def test_advect_vec4_matches_per_cell_kernel_256(lib, monkeypatch):
+    """The float4 advect kernel (shared-displacement fast path + per-cell gathers) against the per-cell kernel on a 256^3
+    plume-like state: bit identical."""
+    rng = np.random.default_rng(31)
+    n = 256
+    shape = (n, n, n)
+    f = {nme: P.rnd(shape, rng, 0.02) for nme in ("vx0", "vy0", "vz0")}
+    f["vy0"][96:160, 40:120, 96:160] += np.float32(3.0)          # a fast core, sub-cell motion elsewhere
+    f["vx0"][:, :, : n // 2] = np.abs(f["vx0"][:, :, : n // 2])
+    f["vz0"][: n // 3] = 0
+    mask = P.random_mask(shape, rng, 0.01)
+    out = {}
+    for tag, env in (("vec4", "0"), ("cell", "1")):
+        monkeypatch.setenv("FS_NO_ADVECT_VEC4", env)
+        with P.make_solver(lib, n, n, n) as s:
+            s.set_obstacles(mask)
+            for nme, a in f.items():
+                s.set_field(nme, a)
+            s.op_advect_velocity(0.025)
+            s.set_field("vx0", f["vx0"])
+            s.op_advect("density", "vx0", 0, 0.025)
+            out[tag] = {nme: s.get_field(nme) for nme in ("vx", "vy", "vz", "density")}
+    for nme in out["vec4"]:
+        P.assert_exact(out["vec4"][nme], out["cell"][nme], f"advect vec4 vs per-cell {nme}")
 
 
 @pytest.mark.parametrize("dims", [(16, 12, 1), (64, 40, 35)])
