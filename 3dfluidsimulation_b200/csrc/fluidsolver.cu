@@ -106,6 +106,7 @@ struct CudaExec {
         if (const char *e = getenv("FS_PAIR_ROWS")) pair_rows = atoi(e);
         if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
+        if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -124,6 +125,8 @@ struct CudaExec {
         if (scratch) cudaFree(scratch);
         if (render_buf) cudaFree(render_buf);
         render_buf = nullptr; render_bytes = 0;
+        if (tile_cum) cudaFree(tile_cum);
+        tile_cum = nullptr;
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -245,6 +248,8 @@ struct CudaExec {
         if (g.nx % 4 == 0 && !force_generic && c_ok) {
             FsRelaxBatch batch{};
             batch.nf = nf;
+            FsTileMap tiles{};
+            if (flags && tile_cum && !no_tilemap) { tiles.cum = tile_cum; tiles.tx_count = tile_tx; tiles.ty_count = tile_ty; }
             for (int f = 0; f < nf; f++) {
                 batch.in[f] = in[f]; batch.rhs[f] = rhs ? rhs[f] : nullptr; batch.stale[f] = stale ? stale[f] : nullptr;
                 batch.out[f] = out[f]; batch.b[f] = b[f];
@@ -271,7 +276,7 @@ struct CudaExec {
             const dim3 block(bx, by, 1);
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
-         relax_vec4<MODE_, HZ_><<<grid, block, 0, st>>>(g, batch, flags, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
+         relax_vec4<MODE_, HZ_><<<grid, block, 0, st>>>(g, batch, flags, tiles, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); \
          launches++; } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
@@ -511,7 +516,22 @@ struct CudaExec {
         const int nx = g.nx, ny = g.ny;
         linear(count, [=] __device__(long long t) { fs_streamline_glyph(nx, ny, skip, scale, ux, uy, mask, (int)t, out + 4 * t); });
     }
+    // coarse obstacle map for the sweeps (fs_kernels.cuh FsTileMap), rebuilt with the flags
+    int *tile_cum = nullptr;
+    int tile_tx = 0, tile_ty = 0;
+    bool no_tilemap = false; // FS_NO_TILEMAP=1 (experiments)
     void build_flags(const FsGrid &g, const uint8_t *mask, uint8_t *flags) {
+        if (tile_cum) { cudaStreamSynchronize(st); cudaFree(tile_cum); tile_cum = nullptr; }
+        if (g.nx % 4 == 0) {
+            tile_tx = (g.nx + FS_TILE_X - 1) / FS_TILE_X;
+            tile_ty = (g.ny - 2 + FS_TILE_Y - 1) / FS_TILE_Y;
+            const long long ntiles = (long long)tile_tx * tile_ty;
+            tile_cum = (int *)alloc(sizeof(int) * (size_t)(ntiles * (g.nzl + 1)));
+            if (tile_cum) {
+                build_tilemap_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(g, mask, tile_cum, tile_tx, tile_ty);
+                launches++;
+            }
+        }
         const long long n = g.sz * g.nzl;
         linear(n, [=] __device__(long long t) {
             const int i = (int)(t % g.nx), j = (int)((t / g.nx) % g.ny), kl = (int)(t / g.sz);

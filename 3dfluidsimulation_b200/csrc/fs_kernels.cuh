@@ -264,10 +264,40 @@ struct FsRelaxBatch {
     int b[FS_BATCH];
     int nf;
 };
+// Coarse obstacle map: for every tile of FS_TILE_X x FS_TILE_Y cells (interior rows counted from j = 1) the running count
+// along z of planes in which the tile holds an obstacle cell: cum[kl][ty][tx] = number of such planes below local plane
+// kl (nzl + 1 entries per tile).  A sweep CTA whose tile is obstacle free over all its planes (two loads, one compare
+// before the z loop) skips the flag stream altogether: 1 of the 13 B/voxel of a Jacobi sweep, 1 of 9 for the smoother.
+#define FS_TILE_X 128
+#define FS_TILE_Y 8
+struct FsTileMap {
+    const int *cum; // nullptr: no map, always stream the flags
+    int tx_count, ty_count;
+};
+__global__ void __launch_bounds__(256)
+build_tilemap_kernel(const FsGrid g, const uint8_t *__restrict__ mask, int *cum, int tx_count, int ty_count) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per tile column, marching in z
+    if (t >= tx_count * ty_count) return;
+    const int tx = t % tx_count, ty = t / tx_count;
+    const int x_lo = tx * FS_TILE_X, x_hi = min(x_lo + FS_TILE_X, g.nx);
+    const int j_lo = 1 + ty * FS_TILE_Y, j_hi = min(j_lo + FS_TILE_Y, g.ny - 1);
+    int count = 0;
+    for (int kl = 0; kl < g.nzl; kl++) {
+        cum[(long long)kl * tx_count * ty_count + t] = count;
+        int any = 0;
+        for (int j = j_lo; j < j_hi && !any; j++) {
+            const uint32_t *row = reinterpret_cast<const uint32_t *>(mask + fs_idx(g, 0, j, kl)); // nx % 4 == 0 here
+            for (int x = x_lo; x < x_hi; x += 4)
+                if (row[x >> 2]) { any = 1; break; }
+        }
+        count += any;
+    }
+    cum[(long long)g.nzl * tx_count * ty_count + t] = count;
+}
 template <int MODE, bool HZ>
 __global__ void __launch_bounds__(256, 4)
-relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const float a, const float c,
-           const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
+relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
+           const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
            const int zc_stride, const int l2_ahead) {
     const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
     const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
@@ -301,6 +331,12 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     const float *pin = in + idx0;
     const float *prh = rhs ? rhs + idx0 : nullptr;
     const uint8_t *pfl = flags ? flags + idx0 : nullptr;
+    bool use_fl = flags != nullptr;                       // (pfl is advanced every plane, so it cannot be the test)
+    if (use_fl && tiles.cum) { // this tile is obstacle free over all of this CTA's planes: no flag stream
+        const long long tstep = (long long)tiles.ty_count * tiles.tx_count;
+        const int *tc = tiles.cum + ((j - 1) / FS_TILE_Y) * tiles.tx_count + x0 / FS_TILE_X;
+        use_fl = __ldg(tc + k_hi * tstep) != __ldg(tc + k_lo * tstep);
+    }
     float *pout = out + idx0;
     const long long sy = g.sy, sz = g.sz;
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
@@ -323,11 +359,11 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
             // start the DRAM->L2 transfers of a later iteration now; unlike a register prefetch this holds no registers
             if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
             if (MODE == FS_MODE_JACOBI) prefetch_l2(prh + (long long)l2_ahead * sz);
-            if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
+            if (use_fl) prefetch_l2(pfl + (long long)l2_ahead * sz);
         }
         float4 r4 = cur;
         if (MODE == FS_MODE_JACOBI) r4 = ld4_stream(prh);
-        const uint32_t fl = flags ? ld_flags4(pfl) : 0u;
+        const uint32_t fl = use_fl ? ld_flags4(pfl) : 0u;
 
         const float cv[6] = {left, cur.x, cur.y, cur.z, cur.w, right};
         const float upv[4] = {up.x, up.y, up.z, up.w}, dnv[4] = {dn.x, dn.y, dn.z, dn.w};

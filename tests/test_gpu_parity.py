@@ -370,14 +370,22 @@ def test_cpp_host_on_gpu(lib, tmp_path):
     subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"),
                     os.path.join(ROOT, "tests", "cpp", "host_demo.cpp"), "-o", exe, "-L", os.path.dirname(lib), "-lfluidsolver",
                     f"-Wl,-rpath,{os.path.dirname(lib)}", "-Wl,-rpath-link,/usr/local/cuda/lib64"], check=True)
-    out = subprocess.run([exe, "64", "3", "1"], capture_output=True, text=True, check=True).stdout
-    got = {l.split()[0]: [float(v) for v in l.split()[1:]] for l in out.strip().splitlines()}
-    sim = P.pkg().FluidSimulation(size=64, lib_path=lib, use_cuda_graph=False)
-    sim.enableCustomSource = True; sim.sourceEmitsVelocity = True
-    sim.sourceDirection = 90.0; sim.sourceRadius = 2.0; sim.sourcePositionY = 0.2
-    for _ in range(3):
-        sim.Update()
-    for name in ("density", "vx", "vy", "pressure"):
-        a = sim.field(name).astype(np.float64)
-        np.testing.assert_allclose(got[name], [a.sum(), (a * a).sum()], rtol=2e-5, atol=1e-12, err_msg=name)
-    sim.close()
+    for size, frames, depth, shape in ((64, 3, 1, 0), (48, 2, 16, 2)):
+        out = subprocess.run([exe, str(size), str(frames), str(depth), str(shape)], capture_output=True, text=True, check=True).stdout
+        got = {l.split()[0]: [float(v) for v in l.split()[1:]] for l in out.strip().splitlines()}
+        sim = P.pkg().FluidSimulation(size=size, depth=depth, obstacleShape=["Circle", "Rectangle", "Airfoil"][shape], lib_path=lib,
+                                      use_cuda_graph=False)
+        sim.enableCustomSource = True; sim.sourceEmitsVelocity = True
+        sim.sourceDirection = 90.0; sim.sourceRadius = 2.0; sim.sourcePositionY = 0.2
+        for f in range(frames):
+            sim.AddForceToArea((np.float32(0.3) * np.float32(size) + np.float32(f), np.float32(0.6) * np.float32(size)), (2.5, -1.25), 3.0)
+            sim.Update()
+        assert int(sim.obstacles.sum()) == int(got["obstacle_cells"][0])
+        for name in ("density", "vx", "vy", "pressure"):
+            a = sim.field(name).astype(np.float64)
+            np.testing.assert_allclose(got[name], [a.sum(), (a * a).sum()], rtol=2e-5, atol=1e-12, err_msg=name)
+        vis = P.pkg().native.FsVisParams.reference_defaults(size, 2)
+        rgba = sim.UpdateVisualization(vis).astype(np.float64)
+        np.testing.assert_allclose(got["rgba"], [rgba.sum(), (rgba * rgba).sum()], rtol=2e-5, err_msg="rgba")
+        assert int(sim.DrawStreamlines().sum()) == int(got["streamline_pixels"][0])
+        sim.close()
