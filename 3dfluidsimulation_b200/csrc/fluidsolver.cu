@@ -528,8 +528,9 @@ struct CudaExec {
             const long long ntiles = (long long)tile_tx * tile_ty;
             tile_cum = (int *)alloc(sizeof(int) * (size_t)(ntiles * (g.nzl + 1)));
             if (tile_cum) {
-                build_tilemap_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(g, mask, tile_cum, tile_tx, tile_ty);
-                launches++;
+                tilemap_mark_kernel<<<(unsigned)((ntiles * g.nzl + 255) / 256), 256, 0, st>>>(g, mask, tile_cum, tile_tx, tile_ty);
+                tilemap_scan_kernel<<<(unsigned)((ntiles + 255) / 256), 256, 0, st>>>(tile_cum, (int)ntiles, g.nzl);
+                launches += 2;
             }
         }
         const long long n = g.sz * g.nzl;

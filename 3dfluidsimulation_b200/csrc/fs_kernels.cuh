@@ -274,25 +274,35 @@ struct FsTileMap {
     const int *cum; // nullptr: no map, always stream the flags
     int tx_count, ty_count;
 };
+// step 1: cum[kl + 1][tile] = 1 if the tile holds an obstacle cell in local plane kl (one thread per tile and plane)
 __global__ void __launch_bounds__(256)
-build_tilemap_kernel(const FsGrid g, const uint8_t *__restrict__ mask, int *cum, int tx_count, int ty_count) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per tile column, marching in z
-    if (t >= tx_count * ty_count) return;
-    const int tx = t % tx_count, ty = t / tx_count;
+tilemap_mark_kernel(const FsGrid g, const uint8_t *__restrict__ mask, int *cum, int tx_count, int ty_count) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long ntiles = (long long)tx_count * ty_count;
+    if (t >= ntiles * g.nzl) return;
+    const int kl = (int)(t / ntiles), tile = (int)(t % ntiles);
+    const int tx = tile % tx_count, ty = tile / tx_count;
     const int x_lo = tx * FS_TILE_X, x_hi = min(x_lo + FS_TILE_X, g.nx);
     const int j_lo = 1 + ty * FS_TILE_Y, j_hi = min(j_lo + FS_TILE_Y, g.ny - 1);
-    int count = 0;
-    for (int kl = 0; kl < g.nzl; kl++) {
-        cum[(long long)kl * tx_count * ty_count + t] = count;
-        int any = 0;
-        for (int j = j_lo; j < j_hi && !any; j++) {
-            const uint32_t *row = reinterpret_cast<const uint32_t *>(mask + fs_idx(g, 0, j, kl)); // nx % 4 == 0 here
-            for (int x = x_lo; x < x_hi; x += 4)
-                if (row[x >> 2]) { any = 1; break; }
-        }
-        count += any;
+    int any = 0;
+    for (int j = j_lo; j < j_hi && !any; j++) {
+        const uint32_t *row = reinterpret_cast<const uint32_t *>(mask + fs_idx(g, 0, j, kl)); // nx % 4 == 0 here
+        for (int x = x_lo; x < x_hi; x += 4)
+            if (row[x >> 2]) { any = 1; break; }
     }
-    cum[(long long)g.nzl * tx_count * ty_count + t] = count;
+    cum[(kl + 1) * ntiles + tile] = any;
+}
+// step 2: running count along z, in place (one thread per tile)
+__global__ void __launch_bounds__(256)
+tilemap_scan_kernel(int *cum, int ntiles, int nzl) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= ntiles) return;
+    int count = 0;
+    cum[t] = 0;
+    for (int kl = 1; kl <= nzl; kl++) {
+        count += cum[(long long)kl * ntiles + t];
+        cum[(long long)kl * ntiles + t] = count;
+    }
 }
 template <int MODE, bool HZ>
 __global__ void __launch_bounds__(256, 4)
@@ -570,11 +580,7 @@ relax_pair_kernel(const FsGrid g, const float *__restrict__ in, const float *__r
             }
             if (KIND != FS_PAIR_SMOOTH) r4 = ld4_stream(prh);
             fl = flags ? ld_flags4(pfl) : 0u;
-            if (l2_ahead > 0 && kl + l2_ahead <= k_hi) {
-                if (!in_zero) prefetch_l2(pin + (long long)(l2_ahead + 1) * sz);
-                if (KIND != FS_PAIR_SMOOTH) prefetch_l2(prh + (long long)l2_ahead * sz);
-                if (flags) prefetch_l2(pfl + (long long)l2_ahead * sz);
-            }
+            // (no prefetch.global.L2 here: measured without effect on this kernel, profiles/r02b_pair_kernel.md)
         }
         // ---------------- (2) stage 2 at plane kl - 2 ----------------
         if (inner && kl - 2 >= k_lo && kl - 2 < k_hi) {
@@ -582,11 +588,15 @@ relax_pair_kernel(const FsGrid g, const float *__restrict__ in, const float *__r
             float4 up2 = s_r[cols], dn2 = s_r[-cols];
             const float left2 = s_r[-1].w, right2 = s_r[1].x;
             float4 zp = y_a, zn = y_c;
-            if (KIND != FS_PAIR_RED_BLACK) {             // set_bnd y / z faces of the intermediate field, on the fly
-                if (j == 1) dn2 = make_float4(sgn_y * y_b.x, sgn_y * y_b.y, sgn_y * y_b.z, sgn_y * y_b.w);
-                if (j == g.ny - 2) up2 = make_float4(sgn_y * y_b.x, sgn_y * y_b.y, sgn_y * y_b.z, sgn_y * y_b.w);
-                if (k2 == 1) zp = make_float4(sgn_z * y_b.x, sgn_z * y_b.y, sgn_z * y_b.z, sgn_z * y_b.w);
-                if (k2 == g.nz - 2) zn = make_float4(sgn_z * y_b.x, sgn_z * y_b.y, sgn_z * y_b.z, sgn_z * y_b.w);
+            const bool zface = k2 == 1 || k2 == g.nz - 2;
+            if (KIND != FS_PAIR_RED_BLACK && (yface || zface)) { // set_bnd y / z faces of the intermediate field, on the fly
+                // (a real branch: as predicated multiplies these 16 instructions cost every warp their issue slots)
+                const float4 ys = make_float4(sgn_y * y_b.x, sgn_y * y_b.y, sgn_y * y_b.z, sgn_y * y_b.w);
+                const float4 zs4 = make_float4(sgn_z * y_b.x, sgn_z * y_b.y, sgn_z * y_b.z, sgn_z * y_b.w);
+                if (j == 1) dn2 = ys;
+                if (j == g.ny - 2) up2 = ys;
+                if (k2 == 1) zp = zs4;
+                if (k2 == g.nz - 2) zn = zs4;
             }
             const float4 rr = KIND == FS_PAIR_SMOOTH ? y_b : r_pp;
             const float cv[6] = {left2, y_b.x, y_b.y, y_b.z, y_b.w, right2};
@@ -604,7 +614,7 @@ relax_pair_kernel(const FsGrid g, const float *__restrict__ in, const float *__r
                 if (KIND == FS_PAIR_RED_BLACK) keep = keep || (((l + par) & 1) == 0);
                 v[l] = keep ? cv[l + 1] : val;
             }
-            if (!yface && k2 != 1 && k2 != g.nz - 2) {
+            if (!yface && !zface) {
                 if (first_x) v[0] = sgn_x * v[1];
                 if (last_x) v[3] = sgn_x * v[2];
                 st4(pout, v);
@@ -763,16 +773,23 @@ advect_vec4(const FsGrid g, const FsAdvectBatch ab, const float *__restrict__ ve
     FsAdvectWeights w[4];
 #pragma unroll
     for (int l = 0; l < 4; l++) w[l] = fs_advect_weights(g, dt0, uxv[l], uyv[l], uzv[l], x0 + l, j, kl + g.zoff);
-    const int di = w[0].i0 - x0;
+    // shared displacement of the INTERIOR lanes (the x-face lanes x = 0 / nx-1 are ring cells: not advected, their velocity
+    // carries set_bnd's sign flip, and letting them veto the fast path sent half the warps of a 512-wide grid down the
+    // gather path)
+    const int di = pos.first_x ? w[1].i0 - (x0 + 1) : w[0].i0 - x0;   // (selects, not w[lr]: a dynamic index would put w in local memory)
+    const int j0 = pos.first_x ? w[1].j0 : w[0].j0, k0 = pos.first_x ? w[1].k0 : w[0].k0;
     bool uniform = di == 0 || di == -1;
 #pragma unroll
-    for (int l = 1; l < 4; l++) uniform = uniform && (w[l].i0 - (x0 + l) == di) && w[l].j0 == w[0].j0 && w[l].k0 == w[0].k0;
+    for (int l = 0; l < 4; l++) {
+        const bool ring_lane = (l == 0 && pos.first_x) || (l == 3 && pos.last_x);
+        uniform = uniform && (ring_lane || ((w[l].i0 - (x0 + l) == di) && w[l].j0 == j0 && w[l].k0 == k0));
+    }
 #pragma unroll
     for (int f = 0; f < NF; f++) {
         const FsSlabView &sv = ab.src[f];
         float v[4];
         if (uniform) {
-            const float *p0 = fs_slab_plane(sv, g, w[0].k0) + w[0].j0 * g.sy;
+            const float *p0 = fs_slab_plane(sv, g, k0) + j0 * g.sy;
             float A[5], B[5];
             fs_row5(p0, x0, di, pos.first_x, pos.last_x, A);
             fs_row5(p0 + g.sy, x0, di, pos.first_x, pos.last_x, B);
@@ -781,7 +798,7 @@ advect_vec4(const FsGrid g, const FsAdvectBatch ab, const float *__restrict__ ve
             for (int l = 0; l < 4; l++)
                 lo[l] = w[l].s0 * (w[l].t0 * A[l] + w[l].t1 * B[l]) + w[l].s1 * (w[l].t0 * A[l + 1] + w[l].t1 * B[l + 1]);
             if (HZ) {
-                const float *p1 = fs_slab_plane(sv, g, w[0].k0 + 1) + w[0].j0 * g.sy;
+                const float *p1 = fs_slab_plane(sv, g, k0 + 1) + j0 * g.sy;
                 float C[5], D[5];
                 fs_row5(p1, x0, di, pos.first_x, pos.last_x, C);
                 fs_row5(p1 + g.sy, x0, di, pos.first_x, pos.last_x, D);
