@@ -41,7 +41,7 @@ struct CudaExec {
     int pair_mode = 2;          // FS_PAIR: 0 never use the fused two-stage sweep, 1 always, 2 auto (see pair_supported)
     bool pair_force = false;
     bool no_advect_vec4 = false; // FS_NO_ADVECT_VEC4=1: per-cell advect kernels (tests compare both)
-    bool pair_slabs = true;     // FS_PAIR_SLABS=0: auto mode does not fuse Jacobi / smoother sweeps on z-slabs
+    bool pair_slabs = false;    // FS_PAIR_SLABS=1: auto mode also fuses Jacobi / smoother sweeps on z-slabs (measured slower at N = 2: 56.9 vs 47.3 ms/step)
     int l2_ahead = 2;           // prefetch.global.L2 of the planes n steps ahead in the sweep (FS_L2_AHEAD overrides; 0 = off).
                                 // measured 512^3: Jacobi 297 -> 246 us, smoother 256 -> 224 us (profiles/r01f_l2_prefetch.md)
     bool use_graph = false;
@@ -315,9 +315,9 @@ struct CudaExec {
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
     // Policy (FS_PAIR = 0 never / 1 always / unset: auto).  Measured on B200 (profiles/r02b_pair_kernel.md): the fused
     // kernel moves 13 B/voxel per two stages but is issue bound -- 0.64 ms per Jacobi pair at 512^3 against 2 x 0.26 ms
-    // for two single sweeps that already run at the HBM roofline; the red-black form beats its two-launch version
-    // (0.66 vs 0.75 ms).  So auto = red-black always; Jacobi / smoother pairs only on z-slabs, where halving the number
-    // of launches and halo exchanges is worth more than the issue cost.
+    // for two single sweeps that already run at the HBM roofline, and on two z-slabs 56.9 vs 47.3 ms per step; the
+    // red-black form beats its two-launch version (0.66 vs 0.75 ms).  So auto = red-black only (FS_PAIR_SLABS=1 adds
+    // Jacobi / smoother pairs on z-slabs for experiments).
     bool pair_supported(const FsGrid &g, float c, int kind) const {
         const bool c_ok = c != 0.0f && c == c && c - c == 0.0f;
         if (!(g.hz && g.nx % 4 == 0 && !force_generic && c_ok)) return false;

@@ -14,8 +14,12 @@ run() { # name, extra env, bench args
   echo "$name rc=$?"; tail -c 600 gpurun_out/r2m_${name}_$N.err | tail -2
 }
 run b512 "FS_X=0" --steps 10 --warmup 3
-run b512_nopair "FS_PAIR=0" --steps 10 --warmup 3 --no-extra
+run b512_pairslabs "FS_PAIR_SLABS=1" --steps 10 --warmup 3 --no-extra
 run b512_weak "FS_X=0" --steps 5 --warmup 3 --scaling weak --no-extra --no-kernels
+if [ "$N" = "8" ]; then
+  run b1024 "FS_X=0" --steps 5 --warmup 3 --workload 1024 --no-extra
+  run b1024rb "FS_X=0" --steps 5 --warmup 3 --workload 1024rb --no-extra
+fi
 python - <<PY
 import json,glob
 for f in sorted(glob.glob('gpurun_out/r2m_*_$N.json')):
