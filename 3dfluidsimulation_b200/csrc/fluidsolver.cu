@@ -90,7 +90,14 @@ struct CudaExec {
         if (device < 0 || device >= count) { msg = "device_id out of range"; bad = true; return 1; }
         FS_CUDA(cudaSetDevice(dev));
         FS_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        FS_CUDA(cudaStreamCreateWithFlags(&st_halo, cudaStreamNonBlocking));
+        {   // the halo stream runs the boundary chunks of a sweep and the push beside the interior launch: its CTAs must be
+            // dispatched FIRST (highest priority), otherwise they queue behind the interior CTAs and the exchange is serialised
+            // after the sweep instead of hidden behind it
+            int prio_lo = 0, prio_hi = 0;
+            FS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+            const char *np = getenv("FS_HALO_NO_PRIORITY");
+            FS_CUDA(cudaStreamCreateWithPriority(&st_halo, cudaStreamNonBlocking, (np && np[0] == '1') ? prio_lo : prio_hi));
+        }
         FS_CUDA(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         FS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
@@ -742,6 +749,12 @@ struct CudaExec {
         int nzl = 0, kb = 0, ke = 0, zoff = 0, dev = -1;
     };
     bool halo_on = false;
+    // FS_HALO_TRACE=<path prefix>: every halo operation records four %globaltimer stamps (start, previous op of the
+    // neighbours seen, planes stored, neighbours' planes landed); halo_close() writes <prefix>.rank<r>.csv
+    static const unsigned kHaloTraceCap = 1u << 16;
+    unsigned long long *halo_trace = nullptr;
+    std::string halo_trace_path;
+    int halo_rank = 0;
     Peer lo, hi;
     unsigned *my_flags = nullptr;       // FS_HF_WORDS words, device
     std::vector<float *> bufs;          // this slab's field allocations, same order on every rank
@@ -758,6 +771,8 @@ struct CudaExec {
         h.my_flags = my_flags;
         h.op_offset = op_offset;
         h.nf = nf;
+        h.trace = halo_trace;
+        h.trace_cap = kHaloTraceCap;
         if (lo.present) h.lo_flags = lo.flags;
         if (hi.present) h.hi_flags = hi.flags;
         for (int f = 0; f < nf; f++) {
@@ -865,10 +880,32 @@ struct CudaExec {
         if (rc == FS_OK && upper_blob) rc = connect_one(hi, upper_blob, r + 1, same_process);
         if (rc != FS_OK) return rc;
         halo_on = true;
+        halo_rank = r;
+        if (const char *tp = getenv("FS_HALO_TRACE")) {
+            halo_trace_path = tp;
+            halo_trace = (unsigned long long *)alloc(sizeof(unsigned long long) * 4 * kHaloTraceCap);
+            if (halo_trace) FS_CUDA(cudaMemset(halo_trace, 0, sizeof(unsigned long long) * 4 * kHaloTraceCap));
+        }
         invalidate_graph();
         return FS_OK;
     }
+    void halo_trace_dump() {
+        if (!halo_trace) return;
+        std::vector<unsigned long long> h(4 * (size_t)kHaloTraceCap);
+        if (cudaMemcpy(h.data(), halo_trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost) == cudaSuccess) {
+            const std::string path = halo_trace_path + ".rank" + std::to_string(halo_rank) + ".csv";
+            if (FILE *f = fopen(path.c_str(), "w")) {
+                fprintf(f, "slot,start_ns,prev_seen_ns,stored_ns,landed_ns\n");
+                for (unsigned i = 0; i < kHaloTraceCap; i++)
+                    if (h[4 * i]) fprintf(f, "%u,%llu,%llu,%llu,%llu\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
+                fclose(f);
+            }
+        }
+        cudaFree(halo_trace);
+        halo_trace = nullptr;
+    }
     void halo_close() {
+        halo_trace_dump();
         for (Peer *p : {&lo, &hi}) {
             if (p->present && p->ipc) {
                 for (float *b : p->base) if (b) cudaIpcCloseMemHandle(b);

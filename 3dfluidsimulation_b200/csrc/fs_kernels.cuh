@@ -148,6 +148,8 @@ struct FsHaloArgs {
     unsigned *lo_flags;              // neighbours' flag blocks (peer memory)
     unsigned *hi_flags;
     unsigned op_offset;
+    unsigned long long *trace;       // optional (FS_HALO_TRACE): 4 %globaltimer stamps per operation, ring of trace_cap entries
+    unsigned trace_cap;
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
@@ -191,8 +193,11 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) {
         const unsigned seq = halo_seq(h);
+        unsigned long long *tr = (h.trace && blockIdx.x == 0) ? h.trace + 4ull * (seq % h.trace_cap) : nullptr;
+        if (tr) tr[0] = fs_globaltimer_ns();             // kernel start
         if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
         if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
+        if (tr) tr[1] = fs_globaltimer_ns();             // neighbours' previous operation seen
         s_seq = seq;
     }
     __syncthreads();
@@ -217,12 +222,15 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
         if (atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == gridDim.x - 1) {
             h.my_flags[FS_HF_CNT_LO] = 0;
             __threadfence_system();
+            unsigned long long *tr = h.trace ? h.trace + 4ull * (s_seq % h.trace_cap) : nullptr;
+            if (tr) tr[2] = fs_globaltimer_ns();         // all planes stored
             if (h.lo_flags) st_release_sys(h.lo_flags + FS_HF_FROM_HI, s_seq);
             if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
             // ... and do not retire before the neighbours' planes of the same op have landed here: whatever
             // is ordered after this kernel may read the ghost planes (no separate wait launch needed)
             if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
             if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
+            if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed
         }
     }
 }

@@ -12,11 +12,12 @@ the N GPUs (strong scaling: the grid is fixed; --scaling weak keeps 512 x 512 x 
 The state (6 GB) is far larger than L2, so no explicit L2 flush is needed between timed steps.
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
-  roofline      the kernel with the largest share of the step (the fused two-stage Jacobi sweep when the grid takes
-                it, else the single Jacobi sweep): COMPULSORY bytes per launch (in 4 + rhs 4 + flags 1 + out 4 =
-                13 B/voxel) / average launch duration (CUDA events on the solver's stream, back-to-back launches on
-                the live fields right after the timed steps) against MEASURED_PEAKS.json hbm_gbs; `kernels` lists
-                the same figure for every kernel of the step; traffic = ncu dram bytes (profiles/).
+  roofline      the kernel with the largest share of the step (the Jacobi sweep relax_vec4; the fused single-pass sweep
+                when the solver is red-black): ALGORITHMIC bytes per launch (in 4 + rhs 4 + flags 1 + out 4 =
+                13 B/voxel) / average launch duration (CUDA events on the solver's stream, back-to-back
+                launches on the live fields right after the timed steps) against MEASURED_PEAKS.json hbm_gbs; `kernels`
+                lists the same figure for every kernel (in_step: launched by the default policy); traffic = ncu dram
+                bytes per launch (profiles/).
   cpu_baseline  the CPU oracle (C restatement of FluidSim.cs, OpenMP, all host cores) on a bounded sample: a
                 z-slab of the SAME nx x ny grid (same rows, same coefficients) with 256^3 voxels' worth of planes;
                 "port-tidy" = oracle/fluid_oracle.c, "port-faithful" = oracle/ref_faithful3d.c (static-64 job
@@ -475,7 +476,7 @@ def main():
         (6, "gradient_vec4", "ProjectVelocityAdjustJob + 3 BoundaryJob", 28 + fl, 1),
     ]
     kernels = []
-    measure = [7, 1, 0] if args.no_kernels else [k[0] for k in kernel_table]
+    measure = [1, 0] + ([9] if kind else []) if args.no_kernels else [k[0] for k in kernel_table]
     if world > 1:
         measure = [k for k in measure if k in (0, 1, 2, 7, 8, 9)]   # the once-per-step kernels peer-read neighbours' live fields
     order = [k for k in (3, 4, 5, 7, 8, 9, 1, 0, 2, 6) if k in measure]   # gradient last: it overwrites the velocities
@@ -491,7 +492,19 @@ def main():
         kernels.append({"kernel": name, "replaces": job_name, "bytes_per_voxel": bpv, "avg_launch_ms": ms_k,
                         "achieved_GBps": gbs, "frac": gbs / peak, "reference_sweeps_per_launch": nsweeps})
     by_name = {k["kernel"]: k for k in kernels}
-    dom = by_name.get("relax_pair_kernel<RED_BLACK>" if kind else "relax_pair_kernel<JACOBI>") or by_name.get("relax_vec4<JACOBI>")
+    # which kernels the step launches under the default policy (csrc/fluidsolver.cu pair_supported): single sweeps for
+    # Jacobi / smoother, the fused kernel for red-black; the others are listed for comparison
+    fused_env = os.environ.get("FS_PAIR", "")
+    for k in kernels:
+        name = k["kernel"]
+        if name.startswith("relax_pair_kernel"):
+            k["in_step"] = fused_env == "1" or (name.endswith("<RED_BLACK>") and kind == 1 and fused_env != "0")
+        elif name == "rb_vec4 x2":
+            k["in_step"] = kind == 1 and fused_env == "0"
+        else:
+            k["in_step"] = True
+    # the dominant kernel of the workload: the pressure sweep (160 of the 328 sweeps of the 512^3 step)
+    dom = (by_name.get("relax_pair_kernel<RED_BLACK>") if kind else None) or by_name.get("relax_vec4<JACOBI>")
     traffic_key = {"relax_pair_kernel<JACOBI>": "relax_pair_jacobi_3d", "relax_pair_kernel<RED_BLACK>": "relax_pair_rb_3d",
                    "relax_vec4<JACOBI>": "relax_vec4_jacobi_3d"}[dom["kernel"]]
     traffic = ncu_traffic(traffic_key) if (world == 1 and n == 512 and args.scaling == "strong") else None
