@@ -133,6 +133,7 @@ struct CudaExec {
         if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
+        if (const char *e = getenv("FS_FUSED_PUSH")) fused_push = e[0] != '0';
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -300,26 +301,55 @@ struct CudaExec {
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
             const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
             const dim3 block(bx, by, 1);
-#define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
+            FsPushArgs push{};
+#define FS_LAUNCH_RELAX(MODE_, HZ_, PUSH_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
-         launch_on(st, relax_vec4<MODE_, HZ_>, grid, block, g, batch, flags, tiles, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead); } while (0)
-#define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
-    do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
-         else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
-            if (halo_on && fuse_halo && nchunks > 2) {
-                // fork: side stream = boundary chunks, then the P2P push; main stream = interior chunks; join
+         launch_on(st, relax_vec4<MODE_, HZ_, PUSH_>, grid, block, g, batch, flags, tiles, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead, push); } while (0)
+#define FS_LAUNCH_RELAX_MODE(PUSH_, NZ_, BASE_, STRIDE_) \
+    do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, false, NZ_, BASE_, STRIDE_); } \
+         else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, false, NZ_, BASE_, STRIDE_); } } while (0)
+            const bool exchange = halo_on && fuse_halo;
+            if (exchange && fused_push) {
+                // The boundary-chunk launch pushes its own planes (relax_vec4<.., PUSH = true>): wait for the neighbours'
+                // previous op, compute, store local + remote, publish.  One halo operation, no push kernel.
+                push.op_offset = ++ops_since_commit;
+                push.my_flags = my_flags;
+                push.kb = g.kb; push.ke = g.ke;
+                push.side_ctas = (unsigned)(gxn * gyn * nf);
+                if (lo.present) push.lo_flags = lo.flags;
+                if (hi.present) push.hi_flags = hi.flags;
+                for (int f = 0; f < nf; f++) {
+                    const int bi = buf_index(out[f]);
+                    if (lo.present && bi >= 0) push.lo_dst[f] = lo.base[bi] + g.sz * (lo.nzl - FS_GHOST);
+                    if (hi.present && bi >= 0) push.hi_dst[f] = hi.base[bi];
+                }
+                pending_incoming = true;                       // nobody has waited for the neighbours' planes of this op yet
+                if (nchunks > 2) {
+                    FS_CUDA(cudaEventRecord(ev_fork, st));
+                    FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
+                    { cudaStream_t main_st = st; st = st_halo;
+                      FS_LAUNCH_RELAX_MODE(true, 2, 0, nchunks - 1); // the two chunks holding the slab's boundary planes, pushing
+                      st = main_st; }
+                    FS_CUDA(cudaEventRecord(ev_join, st_halo));
+                    FS_LAUNCH_RELAX_MODE(false, nchunks - 2, 1, 1);  // interior chunks, concurrently
+                    FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+                } else {
+                    FS_LAUNCH_RELAX_MODE(true, nchunks, 0, 1);
+                }
+            } else if (exchange && nchunks > 2) {
+                // fork: side stream = boundary chunks, then the P2P push kernel; main stream = interior chunks; join
                 FS_CUDA(cudaEventRecord(ev_fork, st));
                 FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
                 { cudaStream_t main_st = st; st = st_halo;
-                  FS_LAUNCH_RELAX_MODE(2, 0, nchunks - 1);     // the two chunks holding the slab's boundary planes
+                  FS_LAUNCH_RELAX_MODE(false, 2, 0, nchunks - 1);
                   st = main_st; }
                 halo_n_on_stream(g, out, nf, st_halo);         // stores them into the neighbours' ghosts, signals, awaits theirs
                 FS_CUDA(cudaEventRecord(ev_join, st_halo));
-                FS_LAUNCH_RELAX_MODE(nchunks - 2, 1, 1);       // interior chunks, concurrently
+                FS_LAUNCH_RELAX_MODE(false, nchunks - 2, 1, 1);
                 FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join (also required before a graph capture ends)
             } else {
-                FS_LAUNCH_RELAX_MODE(nchunks, 0, 1);
-                if (halo_on && fuse_halo) halo_n_on_stream(g, out, nf, st);
+                FS_LAUNCH_RELAX_MODE(false, nchunks, 0, 1);
+                if (exchange) halo_n_on_stream(g, out, nf, st);
             }
 #undef FS_LAUNCH_RELAX_MODE
 #undef FS_LAUNCH_RELAX
@@ -335,6 +365,14 @@ struct CudaExec {
                 cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
         }
         if (fuse_halo) halo_n_on_stream(g, out, nf, st); // per-cell fallback: push after the whole sweep
+    }
+    // After a run of sweeps whose push is fused into the boundary launch nobody has yet waited for the neighbours' planes
+    // of the LAST sweep: a fence (its own tiny halo op) does, before a kernel that is not a sweep reads the ghost planes.
+    bool fused_push = true;       // FS_FUSED_PUSH=0: separate push kernel per sweep (round-1 form)
+    bool pending_incoming = false;
+    void relax_end() {
+        if (halo_on && pending_incoming) halo_fence();
+        pending_incoming = false;
     }
     // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
@@ -813,6 +851,7 @@ struct CudaExec {
     void halo_n(const FsGrid &g, float *const *fields, int nf) { halo_n_on_stream(g, fields, nf, st); }
     void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream) {
         if (!halo_on) return;
+        pending_incoming = false; // a standalone op starts by waiting for the neighbours' previous op and ends with theirs landed
         const unsigned op = ++ops_since_commit;
         const FsHaloArgs h = halo_args(g, fields, nf, op);
         const long long plane = g.sz * FS_GHOST;

@@ -245,6 +245,7 @@ struct SolverCore {
             in = out;
             sweeps++;
         }
+        ex.relax_end();
         float *res = const_cast<float *>(in);
         tmp = res == A ? B : A;
         x = res;
@@ -264,6 +265,7 @@ struct SolverCore {
             }
             std::swap(rd, wr);
         }
+        ex.relax_end();
         x = rd;
         tmp = wr;
     }
@@ -334,6 +336,7 @@ struct SolverCore {
             ex.relax_n(FS_MODE_JACOBI, g, nf, rdc, x0, nullptr, wr, fl(), a, c, b, false, true);
             for (int f = 0; f < nf; f++) std::swap(rd[f], wr[f]);
         }
+        ex.relax_end();
         for (int f = 0; f < nf; f++) { *x[f] = rd[f]; *scratch[f] = wr[f]; }
     }
     void diffuse(int b, float *&x, const float *x0, float diff, float dt) {

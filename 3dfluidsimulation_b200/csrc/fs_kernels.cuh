@@ -312,11 +312,27 @@ tilemap_scan_kernel(int *cum, int ntiles, int nzl) {
         cum[(long long)kl * ntiles + t] = count;
     }
 }
-template <int MODE, bool HZ>
-__global__ void __launch_bounds__(256, 4)
+// Halo push fused into the boundary-chunk launch of a sweep (PUSH = true instantiation, z-slabs only).  The CTAs of the first
+// and last z chunk wait for the neighbour's previous operation before they read the ghost planes, store every float4 they
+// write into the FS_GHOST boundary planes to the neighbour's ghost planes as well (P2P), and the last CTA of a side to
+// finish publishes the operation's sequence number in the neighbour's flag word.  No separate push kernel, so nothing
+// of the exchange has to squeeze in between the interior CTAs (trace at N = 8, 512^3: the standalone push kernel needed
+// 13 us for 4 MB while the interior launch held the SMs, 22 us in all per sweep on the critical path); the interior
+// launch (PUSH = false, the untouched hot kernel) runs beside it.  The incoming planes are awaited by whoever reads them
+// next: the next sweep's boundary CTAs, or the fence the executor issues after a run of sweeps.
+struct FsPushArgs {
+    float *lo_dst[FS_BATCH];         // lower neighbour's top ghost planes of each output field (my plane kb lands on their first)
+    float *hi_dst[FS_BATCH];         // upper neighbour's bottom ghost planes (my plane ke - FS_GHOST lands on their plane 0)
+    unsigned *my_flags, *lo_flags, *hi_flags;
+    unsigned op_offset;
+    int kb, ke;                      // owned local planes [kb, ke)
+    unsigned side_ctas;              // CTAs per z chunk (all fields): the count that completes a side
+};
+template <int MODE, bool HZ, bool PUSH>
+__global__ void __launch_bounds__(256, PUSH ? 2 : 4)
 relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
            const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
-           const int zc_stride, const int l2_ahead) {
+           const int zc_stride, const int l2_ahead, const FsPushArgs push) {
     const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
     const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
     const float *__restrict__ in = fld == 0 ? batch.in[0] : (fld == 1 ? batch.in[1] : batch.in[2]);
@@ -335,6 +351,25 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     const int k_lo = kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
+    // PUSH: which sides this CTA's planes touch, peer offsets of this field, and the wait for the neighbours' previous op
+    const bool side_lo = PUSH && push.lo_flags && k_lo < k_hi && k_lo < push.kb + FS_GHOST;
+    const bool side_hi = PUSH && push.hi_flags && k_lo < k_hi && k_hi > push.ke - FS_GHOST;
+    long long dlo = 0, dhi = 0;
+    __shared__ unsigned s_push_seq;
+    if (PUSH) {
+        float *lo_dst = fld == 0 ? push.lo_dst[0] : (fld == 1 ? push.lo_dst[1] : push.lo_dst[2]);
+        float *hi_dst = fld == 0 ? push.hi_dst[0] : (fld == 1 ? push.hi_dst[1] : push.hi_dst[2]);
+        // element offset from a cell of my boundary planes to the same cell of the neighbour's ghost planes
+        dlo = ((long long)(size_t)lo_dst - (long long)(size_t)(out + g.sz * push.kb)) / (long long)sizeof(float);
+        dhi = ((long long)(size_t)hi_dst - (long long)(size_t)(out + g.sz * (push.ke - FS_GHOST))) / (long long)sizeof(float);
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            const unsigned seq = *(volatile const unsigned *)(push.my_flags + FS_HF_BASE) + push.op_offset;
+            if (side_lo) halo_spin_until(push.my_flags + FS_HF_FROM_LO, seq - 1, push.my_flags + FS_HF_ERROR);
+            if (side_hi) halo_spin_until(push.my_flags + FS_HF_FROM_HI, seq - 1, push.my_flags + FS_HF_ERROR);
+            s_push_seq = seq;
+        }
+        __syncthreads();
+    }
     if (active) {
     const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
@@ -414,6 +449,10 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
             if (first_x) v[0] = b == 1 ? -v[1] : v[1];
             if (last_x) v[3] = b == 1 ? -v[2] : v[2];
             st4(pout, v);
+            if (PUSH) {
+                if (side_lo && kl < push.kb + FS_GHOST) st4(pout + dlo, v);
+                if (side_hi && kl >= push.ke - FS_GHOST) st4(pout + dhi, v);
+            }
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
             if (first_x) v[0] = v[1];
@@ -430,7 +469,12 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
                     float o[4];
 #pragma unroll
                     for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
-                    st4(out + fs_idx(g, x0, ys[yi], zs[zi]), o);
+                    float *po = out + fs_idx(g, x0, ys[yi], zs[zi]);
+                    st4(po, o);
+                    if (PUSH && zi == 0) { // (the z ring planes are global boundary planes: never part of an exchange)
+                        if (side_lo && kl < push.kb + FS_GHOST) st4(po + dlo, o);
+                        if (side_hi && kl >= push.ke - FS_GHOST) st4(po + dhi, o);
+                    }
                 }
             }
         }
@@ -442,7 +486,12 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
                     if (!((fl >> (8 * l)) & 1u) || (l == 0 && first_x) || (l == 3 && last_x)) continue;
-                    pout[l] = fs_mirror_fused<MODE>(g, in, rhs, (uint8_t)(fl >> (8 * l)), a, c, b, in_zero != 0, v[l], x0 + l, j, kl);
+                    const float mv = fs_mirror_fused<MODE>(g, in, rhs, (uint8_t)(fl >> (8 * l)), a, c, b, in_zero != 0, v[l], x0 + l, j, kl);
+                    pout[l] = mv;
+                    if (PUSH) {
+                        if (side_lo && kl < push.kb + FS_GHOST) pout[l + dlo] = mv;
+                        if (side_hi && kl >= push.ke - FS_GHOST) pout[l + dhi] = mv;
+                    }
                 }
             }
         }
@@ -450,6 +499,22 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
         cur = next;
     }
     } // active
+    if (PUSH) { // publish: every store of this CTA is fenced, the last CTA of a side signals the neighbour
+        if (side_lo || side_hi) __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            if (side_lo && atomicAdd(push.my_flags + FS_HF_CNT_LO, 1u) == push.side_ctas - 1) {
+                push.my_flags[FS_HF_CNT_LO] = 0;
+                __threadfence_system();
+                st_release_sys(push.lo_flags + FS_HF_FROM_HI, s_push_seq);
+            }
+            if (side_hi && atomicAdd(push.my_flags + FS_HF_CNT_HI, 1u) == push.side_ctas - 1) {
+                push.my_flags[FS_HF_CNT_HI] = 0;
+                __threadfence_system();
+                st_release_sys(push.hi_flags + FS_HF_FROM_LO, s_push_seq);
+            }
+        }
+    }
 }
 
 // ---- float4 versions of the once-per-step stencils --------------------------------------------------------

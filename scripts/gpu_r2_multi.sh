@@ -14,7 +14,7 @@ run() { # name, extra env, bench args
   echo "$name rc=$?"; tail -c 600 gpurun_out/r2m_${name}_$N.err | tail -2
 }
 run b512 "FS_X=0" --steps 10 --warmup 3
-run b512_pairslabs "FS_PAIR_SLABS=1" --steps 10 --warmup 3 --no-extra
+run b512_sep_push "FS_FUSED_PUSH=0" --steps 10 --warmup 3 --no-extra
 run b512_weak "FS_X=0" --steps 5 --warmup 3 --scaling weak --no-extra --no-kernels
 if [ "$N" = "8" ]; then
   run b1024 "FS_X=0" --steps 5 --warmup 3 --workload 1024 --no-extra

@@ -320,6 +320,7 @@ struct HostExec {
         if (hi.present) spin(hi.seq, op);
     }
     void halo_fence() { halo(FsGrid{}, nullptr); }
+    void relax_end() {}
     void halo_commit() {}
     template <class Core> int halo_export(Core &c, void *blob) {
         if (!my_seq) my_seq = new std::atomic<unsigned>(0);
