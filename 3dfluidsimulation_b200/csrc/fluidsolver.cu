@@ -134,6 +134,7 @@ struct CudaExec {
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
         if (const char *e = getenv("FS_FUSED_PUSH")) fused_push = e[0] != '0';
+        if (const char *e = getenv("FS_PUSH_PLANES")) push_planes = atoi(e);
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -299,12 +300,13 @@ struct CudaExec {
             if (tune_zchunk > 0) zchunk = tune_zchunk; // FS_ZCHUNK (experiments)
             if (zchunk > cnt) zchunk = cnt;
             const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
-            const int iz = in_zero ? 1 : 0, zc = (int)zchunk;
+            const int iz = in_zero ? 1 : 0;
             const dim3 block(bx, by, 1);
             FsPushArgs push{};
+            int kl_b = kl0, kl_e = kl0 + cnt, kl_alt = 0, zc = (int)zchunk; // plane range / chunk length of the next launch
 #define FS_LAUNCH_RELAX(MODE_, HZ_, PUSH_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
-         launch_on(st, relax_vec4<MODE_, HZ_, PUSH_>, grid, block, g, batch, flags, tiles, a, c, iz, kl0, kl0 + cnt, zc, BASE_, STRIDE_, l2_ahead, push); } while (0)
+         launch_on(st, relax_vec4<MODE_, HZ_, PUSH_>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, push, kl_alt); } while (0)
 #define FS_LAUNCH_RELAX_MODE(PUSH_, NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, false, NZ_, BASE_, STRIDE_); } \
          else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, false, NZ_, BASE_, STRIDE_); } } while (0)
@@ -315,7 +317,20 @@ struct CudaExec {
                 push.op_offset = ++ops_since_commit;
                 push.my_flags = my_flags;
                 push.kb = g.kb; push.ke = g.ke;
-                push.side_ctas = (unsigned)(gxn * gyn * nf);
+                {   // chunks of the launch that will push, and how many of them touch each side's FS_GHOST boundary planes
+                    const int zsp = push_planes > FS_GHOST ? push_planes : FS_GHOST;
+                    const bool split = cnt >= 3 * zsp + 2;
+                    int n_lo = 0, n_hi = 0;
+                    if (split) { n_lo = n_hi = 1; }
+                    else
+                        for (int q = 0; q < nchunks; q++) {
+                            const int lo_pl = kl0 + q * (int)zchunk, hi_pl = std::min(lo_pl + (int)zchunk, kl0 + cnt);
+                            if (lo_pl < g.kb + FS_GHOST) n_lo++;
+                            if (hi_pl > g.ke - FS_GHOST) n_hi++;
+                        }
+                    push.side_ctas_lo = (unsigned)(gxn * gyn * nf * n_lo);
+                    push.side_ctas_hi = (unsigned)(gxn * gyn * nf * n_hi);
+                }
                 if (lo.present) push.lo_flags = lo.flags;
                 if (hi.present) push.hi_flags = hi.flags;
                 for (int f = 0; f < nf; f++) {
@@ -324,14 +339,25 @@ struct CudaExec {
                     if (hi.present && bi >= 0) push.hi_dst[f] = hi.base[bi];
                 }
                 pending_incoming = true;                       // nobody has waited for the neighbours' planes of this op yet
-                if (nchunks > 2) {
+                // The pushing instantiation is the slower one (118 registers, 2 CTAs/SM): give it as few planes as the
+                // exchange needs -- two thin chunks of zs planes at the slab's ends -- and everything between to the hot kernel.
+                const int zs = push_planes > FS_GHOST ? push_planes : FS_GHOST;
+                if (cnt >= 3 * zs + 2) {
                     FS_CUDA(cudaEventRecord(ev_fork, st));
                     FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
                     { cudaStream_t main_st = st; st = st_halo;
-                      FS_LAUNCH_RELAX_MODE(true, 2, 0, nchunks - 1); // the two chunks holding the slab's boundary planes, pushing
+                      kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - zs; zc = zs;
+                      FS_LAUNCH_RELAX_MODE(true, 2, 0, 0);          // [kl0, kl0+zs) and [kl0+cnt-zs, kl0+cnt), pushing
                       st = main_st; }
                     FS_CUDA(cudaEventRecord(ev_join, st_halo));
-                    FS_LAUNCH_RELAX_MODE(false, nchunks - 2, 1, 1);  // interior chunks, concurrently
+                    kl_b = kl0 + zs; kl_e = kl0 + cnt - zs;
+                    long long zi = (long long)(cnt - 2 * zs) * blocks_xy * nf / target;
+                    zi = zi < 4 ? 4 : (zi > 16 ? 16 : zi);
+                    if (tune_zchunk > 0) zi = tune_zchunk;
+                    if (zi > cnt - 2 * zs) zi = cnt - 2 * zs;
+                    zc = (int)zi;
+                    const int ni = (int)((cnt - 2 * zs + zi - 1) / zi);
+                    FS_LAUNCH_RELAX_MODE(false, ni, 0, 1);           // everything between, concurrently
                     FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
                 } else {
                     FS_LAUNCH_RELAX_MODE(true, nchunks, 0, 1);
@@ -369,6 +395,7 @@ struct CudaExec {
     // After a run of sweeps whose push is fused into the boundary launch nobody has yet waited for the neighbours' planes
     // of the LAST sweep: a fence (its own tiny halo op) does, before a kernel that is not a sweep reads the ghost planes.
     bool fused_push = true;       // FS_FUSED_PUSH=0: separate push kernel per sweep (round-1 form)
+    int push_planes = 4;          // FS_PUSH_PLANES: planes per end given to the pushing instantiation
     bool pending_incoming = false;
     void relax_end() {
         if (halo_on && pending_incoming) halo_fence();

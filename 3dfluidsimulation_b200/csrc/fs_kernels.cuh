@@ -326,13 +326,13 @@ struct FsPushArgs {
     unsigned *my_flags, *lo_flags, *hi_flags;
     unsigned op_offset;
     int kb, ke;                      // owned local planes [kb, ke)
-    unsigned side_ctas;              // CTAs per z chunk (all fields): the count that completes a side
+    unsigned side_ctas_lo, side_ctas_hi; // CTAs (all fields) whose planes touch the lower / upper boundary planes: the counts that complete a side
 };
 template <int MODE, bool HZ, bool PUSH>
 __global__ void __launch_bounds__(256, PUSH ? 2 : 4)
 relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
            const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
-           const int zc_stride, const int l2_ahead, const FsPushArgs push) {
+           const int zc_stride, const int l2_ahead, const FsPushArgs push, const int kl_alt) {
     const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
     const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
     const float *__restrict__ in = fld == 0 ? batch.in[0] : (fld == 1 ? batch.in[1] : batch.in[2]);
@@ -347,8 +347,9 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     // sweep is issued as two launches of this same kernel -- the two chunks that hold the slab's boundary planes
     // first (base 0, stride nchunks-1), then the interior chunks (base 1, stride 1) -- with the P2P halo push
     // between them, so the exchange overlaps the interior (fluidsolver.cu, CudaExec::relax).
+    // (zc_stride == 0: the two-chunk boundary launch of the fused push -- chunk 0 starts at kl_begin, chunk 1 at kl_alt)
     const int zc = zc_base + zblk * zc_stride;
-    const int k_lo = kl_begin + zc * zchunk;
+    const int k_lo = zc_stride == 0 ? (zblk == 0 ? kl_begin : kl_alt) : kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
     // PUSH: which sides this CTA's planes touch, peer offsets of this field, and the wait for the neighbours' previous op
@@ -503,12 +504,12 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
         if (side_lo || side_hi) __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
-            if (side_lo && atomicAdd(push.my_flags + FS_HF_CNT_LO, 1u) == push.side_ctas - 1) {
+            if (side_lo && atomicAdd(push.my_flags + FS_HF_CNT_LO, 1u) == push.side_ctas_lo - 1) {
                 push.my_flags[FS_HF_CNT_LO] = 0;
                 __threadfence_system();
                 st_release_sys(push.lo_flags + FS_HF_FROM_HI, s_push_seq);
             }
-            if (side_hi && atomicAdd(push.my_flags + FS_HF_CNT_HI, 1u) == push.side_ctas - 1) {
+            if (side_hi && atomicAdd(push.my_flags + FS_HF_CNT_HI, 1u) == push.side_ctas_hi - 1) {
                 push.my_flags[FS_HF_CNT_HI] = 0;
                 __threadfence_system();
                 st_release_sys(push.hi_flags + FS_HF_FROM_LO, s_push_seq);
