@@ -112,8 +112,8 @@ struct CudaExec {
             // after the sweep instead of hidden behind it
             int prio_lo = 0, prio_hi = 0;
             FS_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-            const char *np = getenv("FS_HALO_NO_PRIORITY");
-            halo_prio_attr = !(np && np[0] == '1');
+            const char *np = getenv("FS_HALO_PRIORITY"); // off by default: no effect on graph replay, slightly slower (profiles/r02e_exchange.md)
+            halo_prio_attr = np && np[0] == '1';
             halo_priority = prio_hi;
             FS_CUDA(cudaStreamCreateWithPriority(&st_halo, cudaStreamNonBlocking, halo_prio_attr ? prio_hi : prio_lo));
         }
@@ -135,6 +135,8 @@ struct CudaExec {
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
         if (const char *e = getenv("FS_FUSED_PUSH")) fused_push = e[0] != '0';
         if (const char *e = getenv("FS_PUSH_PLANES")) push_planes = atoi(e);
+        if (const char *e = getenv("FS_EXCHANGE")) exchange_mode = atoi(e);
+        if (const char *e = getenv("FS_SERIAL_MAX_PLANES")) serial_max_planes = atoi(e);
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -362,6 +364,21 @@ struct CudaExec {
                 } else {
                     FS_LAUNCH_RELAX_MODE(true, nchunks, 0, 1);
                 }
+            } else if (exchange && (exchange_mode == 1 || (exchange_mode == 2 && cnt <= serial_max_planes)) && cnt >= 3 * FS_GHOST * 2 + 2) {
+                // serial schedule, one stream: the boundary planes first (two thin chunks), their push without trailing wait,
+                // then everything between; the wait for the neighbours' planes is issued before the NEXT reader of the ghosts
+                const int zs = 2 * FS_GHOST;
+                halo_wait_pending();
+                kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - zs; zc = zs;
+                FS_LAUNCH_RELAX_MODE(false, 2, 0, 0);
+                halo_n_on_stream(g, out, nf, st, /*wait_incoming=*/false);
+                kl_b = kl0 + zs; kl_e = kl0 + cnt - zs;
+                long long zi = (long long)(cnt - 2 * zs) * blocks_xy * nf / target;
+                zi = zi < 4 ? 4 : (zi > 16 ? 16 : zi);
+                if (tune_zchunk > 0) zi = tune_zchunk;
+                if (zi > cnt - 2 * zs) zi = cnt - 2 * zs;
+                zc = (int)zi;
+                FS_LAUNCH_RELAX_MODE(false, (int)((cnt - 2 * zs + zi - 1) / zi), 0, 1);
             } else if (exchange && nchunks > 2) {
                 // fork: side stream = boundary chunks, then the P2P push kernel; main stream = interior chunks; join
                 FS_CUDA(cudaEventRecord(ev_fork, st));
@@ -394,13 +411,20 @@ struct CudaExec {
     }
     // After a run of sweeps whose push is fused into the boundary launch nobody has yet waited for the neighbours' planes
     // of the LAST sweep: a fence (its own tiny halo op) does, before a kernel that is not a sweep reads the ghost planes.
-    bool fused_push = true;       // FS_FUSED_PUSH=0: separate push kernel per sweep (round-1 form)
+    bool fused_push = false;      // FS_FUSED_PUSH=1: the boundary launch pushes its own planes (measured slower, profiles/r02e_exchange.md)
     int push_planes = 4;          // FS_PUSH_PLANES: planes per end given to the pushing instantiation
     bool pending_incoming = false;
     void relax_end() {
         if (halo_on && pending_incoming) halo_fence();
         pending_incoming = false;
+        halo_wait_pending();
     }
+    // Exchange schedule of a sweep on z-slabs (FS_EXCHANGE): 0 fork/join (boundary chunks + push on a side stream beside the
+    // interior launch), 1 serial (one stream: [wait for the previous sweep's incoming planes] -> thin boundary launch ->
+    // push without trailing wait -> interior launch; the neighbours' planes arrive while the interior runs), 2 auto = serial
+    // for thin slabs.  profiles/r02e_exchange.md has the measurements.
+    int exchange_mode = 2;
+    int serial_max_planes = 96;
     // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
     // Policy (FS_PAIR = 0 never / 1 always / unset: auto).  Measured on B200 (profiles/r02b_pair_kernel.md): the fused
@@ -876,16 +900,26 @@ struct CudaExec {
         halo_n_on_stream(g, fields, field ? 1 : 0, stream);
     }
     void halo_n(const FsGrid &g, float *const *fields, int nf) { halo_n_on_stream(g, fields, nf, st); }
-    void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream) {
+    void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream, bool wait_incoming = true) {
         if (!halo_on) return;
-        pending_incoming = false; // a standalone op starts by waiting for the neighbours' previous op and ends with theirs landed
+        // a standalone op starts by waiting for the neighbours' previous op: whatever was left open is closed by it
+        pending_incoming = false;
+        pending_wait_op = 0;
         const unsigned op = ++ops_since_commit;
         const FsHaloArgs h = halo_args(g, fields, nf, op);
         const long long plane = g.sz * FS_GHOST;
         int blocks = (int)((plane / 4 + 255) / 256) * (nf > 1 ? nf : 1);
         if (blocks > sm_count * 2) blocks = sm_count * 2;
         if (blocks < 1 || nf == 0) blocks = 1;
-        launch_on(stream, halo_push_kernel, dim3(blocks), dim3(256), h, nf ? plane : 0LL);
+        launch_on(stream, halo_push_kernel, dim3(blocks), dim3(256), h, nf ? plane : 0LL, wait_incoming ? 1 : 0);
+        if (!wait_incoming) pending_wait_op = op;
+    }
+    // closes a push that did not wait for the neighbours' planes (serial exchange schedule)
+    unsigned pending_wait_op = 0;
+    void halo_wait_pending() {
+        if (!halo_on || !pending_wait_op) return;
+        launch_on(st, halo_wait_kernel, dim3(1), dim3(32), my_flags, lo.present ? 1 : 0, hi.present ? 1 : 0, pending_wait_op);
+        pending_wait_op = 0;
     }
     void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
         if (!halo_on) return;

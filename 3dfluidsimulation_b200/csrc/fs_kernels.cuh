@@ -189,7 +189,7 @@ __device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
 // Copies the FS_GHOST boundary planes of up to FS_BATCH fields into the neighbours' ghost planes (nf = 0: pure fence)
 // after waiting for seq-1, then signals seq and waits for the neighbours' seq.  plane_elems = FS_GHOST*nx*ny.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
+halo_push_kernel(const FsHaloArgs h, long long plane_elems, const int wait_incoming) {
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) {
         const unsigned seq = halo_seq(h);
@@ -228,14 +228,26 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
             if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
             // ... and do not retire before the neighbours' planes of the same op have landed here: whatever
             // is ordered after this kernel may read the ghost planes (no separate wait launch needed)
-            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
-            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
-            if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed
+            if (wait_incoming) {
+                if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
+                if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
+            }
+            if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed (or: not awaited here)
         }
     }
 }
 
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
+
+// The wait a push without trailing wait leaves open: returns once both neighbours have published operation
+// base + op_offset, i.e. their planes of that operation have landed in this slab's ghost planes.
+__global__ void halo_wait_kernel(unsigned *my_flags, const int has_lo, const int has_hi, const unsigned op_offset) {
+    if (threadIdx.x == 0) {
+        const unsigned seq = *(volatile const unsigned *)(my_flags + FS_HF_BASE) + op_offset;
+        if (has_lo) halo_spin_until(my_flags + FS_HF_FROM_LO, seq, my_flags + FS_HF_ERROR);
+        if (has_hi) halo_spin_until(my_flags + FS_HF_FROM_HI, seq, my_flags + FS_HF_ERROR);
+    }
+}
 
 // Gather source for the semi-Lagrangian back-trace: a field as seen from one slab -- its own planes
 // (ghosts included) plus the two neighbour slabs' copies through peer memory (NVLink loads).  A back-trace

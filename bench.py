@@ -371,6 +371,8 @@ def main():
     ap.add_argument("--no-obstacle", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the 1024^3 / weak-scaling side measurements")
     ap.add_argument("--no-kernels", action="store_true", help="skip the per-kernel roofline list")
+    ap.add_argument("--grid", default=None, help="nx,ny,nz override of the workload's grid (experiments: e.g. 512,512,128 on 2 GPUs "
+                                                 "has the slab thickness of 512^3 on 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -403,6 +405,9 @@ def main():
     obstacle = not args.no_obstacle
     graph = not args.no_graph
     dims = (n, n, n * world) if args.scaling == "weak" else (n, n, n)
+    if args.grid:
+        dims = tuple(int(v) for v in args.grid.split(","))
+        cfg += f" [grid overridden: {args.grid}]"
     voxels = dims[0] * dims[1] * dims[2]
 
     check = parity_check(pkg, job, lib) if world > 1 else None
