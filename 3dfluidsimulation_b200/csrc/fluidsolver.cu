@@ -30,7 +30,7 @@ struct CudaExec {
     float *stage[FS_FIELD_COUNT] = {};               // per-field device snapshots the copy stream reads from
     size_t stage_bytes[FS_FIELD_COUNT] = {};
     cudaEvent_t ev_snap[FS_FIELD_COUNT] = {}, ev_sent[FS_FIELD_COUNT] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_ends = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool bad = false;
     std::string msg;
@@ -120,6 +120,7 @@ struct CudaExec {
         FS_CUDA(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         FS_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+        FS_CUDA(cudaEventCreateWithFlags(&ev_ends, cudaEventDisableTiming));
         FS_CUDA(cudaEventCreate(&ev0));
         FS_CUDA(cudaEventCreate(&ev1));
         FS_CUDA(cudaMalloc(&d_sum, sizeof(double)));
@@ -133,10 +134,7 @@ struct CudaExec {
         if (const char *e = getenv("FS_PAIR_ZCHUNK")) pair_zchunk = atoi(e);
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
-        if (const char *e = getenv("FS_FUSED_PUSH")) fused_push = e[0] != '0';
-        if (const char *e = getenv("FS_PUSH_PLANES")) push_planes = atoi(e);
-        if (const char *e = getenv("FS_EXCHANGE")) exchange_mode = atoi(e);
-        if (const char *e = getenv("FS_SERIAL_MAX_PLANES")) serial_max_planes = atoi(e);
+        if (const char *e = getenv("FS_EXTEND")) extend_sweeps = e[0] != '0';
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -161,6 +159,7 @@ struct CudaExec {
         if (ev1) cudaEventDestroy(ev1);
         if (ev_fork) cudaEventDestroy(ev_fork);
         if (ev_join) cudaEventDestroy(ev_join);
+        if (ev_ends) cudaEventDestroy(ev_ends);
         if (st_copy) { cudaStreamSynchronize(st_copy); cudaStreamDestroy(st_copy); }
         for (int f = 0; f < FS_FIELD_COUNT; f++) {
             if (stage[f]) cudaFree(stage[f]);
@@ -171,7 +170,7 @@ struct CudaExec {
         st_copy = nullptr;
         if (st_halo) cudaStreamDestroy(st_halo);
         if (st) cudaStreamDestroy(st);
-        d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = ev_fork = ev_join = nullptr; st = st_halo = nullptr;
+        d_sum = nullptr; d_max = nullptr; scratch = nullptr; ev0 = ev1 = ev_fork = ev_join = ev_ends = nullptr; st = st_halo = nullptr;
     }
 
     // ---- memory -------------------------------------------------------------------------------
@@ -247,6 +246,10 @@ struct CudaExec {
     void cells(const FsGrid &g, F f) {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
+        cells_range(g, kl0, cnt, f);
+    }
+    template <class F>
+    void cells_range(const FsGrid &g, int kl0, int cnt, F f) { // interior rows / columns of local planes [kl0, kl0+cnt)
         if (cnt <= 0) return;
         const dim3 block(64, 4, 1);
         const dim3 grid((g.nx - 2 + 63) / 64, (g.ny - 2 + 3) / 4, cnt);
@@ -261,19 +264,35 @@ struct CudaExec {
     }
 
     // ---- sweeps ----------------------------------------------------------------------------------
+    // xmode (fs_cellops.cuh, FS_X_*): how a sweep on z-slabs relates to the halo exchange.
+    //   FS_X_NONE      owned planes, no exchange
+    //   FS_X_EXCHANGE  owned planes, then the FS_GHOST boundary planes of `out` go to the neighbours (one halo operation)
+    //   FS_X_EXTEND    owned planes PLUS the first ghost plane on each internal side, computed redundantly from the
+    //                  two-deep ghost zone of `in`; no exchange.  An FS_X_EXCHANGE* sweep must follow: it finds `in` valid
+    //                  one plane into the ghost zone, which is all a single sweep reads, and its push restores both planes.
+    //                  Two sweeps per halo operation instead of one.
+    //   FS_X_EXCHANGE_OPEN  as FS_X_EXCHANGE, but the caller promises that the next sweep is an FS_X_EXTEND one: the fork is
+    //                  left open, so that only the boundary chunks of the next sweep wait for the neighbours' planes.
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
-               const uint8_t *flags, float a, float c, int b, bool in_zero, bool fuse_halo) {
+               const uint8_t *flags, float a, float c, int b, bool in_zero, int xmode) {
         const float *ins[1] = {in}, *rhss[1] = {rhs}, *stales[1] = {stale};
         float *outs[1] = {out};
-        relax_n(mode, g, 1, ins, rhss, stales, outs, flags, a, c, &b, in_zero, fuse_halo);
+        relax_n(mode, g, 1, ins, rhss, stales, outs, flags, a, c, &b, in_zero, xmode);
     }
+    bool can_extend(const FsGrid &g) const { return halo_on && g.hz && extend_sweeps; }
     // One sweep over nf <= FS_BATCH fields that share a, c and the flags (the velocity components of a diffusion sweep),
     // in ONE launch and, on z-slabs, ONE halo operation.
     void relax_n(int mode, const FsGrid &g, int nf, const float *const *in, const float *const *rhs, const float *const *stale,
-                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, bool fuse_halo) {
+                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, int xmode) {
         int kl0, cnt;
         interior_planes(g, &kl0, &cnt);
         if (cnt <= 0) return;
+        const bool exchange = halo_on && (xmode == FS_X_EXCHANGE || xmode == FS_X_EXCHANGE_OPEN);
+        const bool extend = halo_on && xmode == FS_X_EXTEND;
+        if (extend) { // one plane into the ghost zone on each side that has a neighbour
+            if (lo.present) { kl0 -= 1; cnt += 1; }
+            if (hi.present) cnt += 1;
+        }
         const bool c_ok = c != 0.0f && c == c && c - c == 0.0f; // finite, non-zero: fs_div's precondition
         if (g.nx % 4 == 0 && !force_generic && c_ok) {
             FsRelaxBatch batch{};
@@ -293,138 +312,104 @@ struct CudaExec {
             const int by = tune_by > 0 ? tune_by : threads / bx; // FS_BLOCK_Y (experiments)
             const int gxn = (groups + bx - 1) / bx, gyn = (g.ny - 2 + by - 1) / by;
             const long long blocks_xy = (long long)gxn * gyn;
-            // z chunk per CTA: short enough for >= ~4 waves of 4 resident CTAs/SM (tail effect), long enough
-            // that re-reading the two halo planes per chunk stays <= 2/16 of one field
             const long long target = (long long)sm_count * 16;
-            long long zchunk = (long long)cnt * blocks_xy * nf / target;
-            if (zchunk < 4) zchunk = 4;
-            if (zchunk > 16) zchunk = 16;
-            if (tune_zchunk > 0) zchunk = tune_zchunk; // FS_ZCHUNK (experiments)
-            if (zchunk > cnt) zchunk = cnt;
-            const int nchunks = (int)((cnt + zchunk - 1) / zchunk);
+            // z chunk per CTA for `planes` planes: short enough for >= ~4 waves of 4 resident CTAs/SM (tail effect), long
+            // enough that re-reading the two halo planes per chunk stays <= 2/16 of one field
+            auto chunk_for = [&](int planes) {
+                long long z = (long long)planes * blocks_xy * nf / target;
+                z = z < 4 ? 4 : (z > 16 ? 16 : z);
+                if (tune_zchunk > 0) z = tune_zchunk; // FS_ZCHUNK (experiments)
+                if (z > planes) z = planes;
+                return (int)z;
+            };
             const int iz = in_zero ? 1 : 0;
             const dim3 block(bx, by, 1);
-            FsPushArgs push{};
-            int kl_b = kl0, kl_e = kl0 + cnt, kl_alt = 0, zc = (int)zchunk; // plane range / chunk length of the next launch
-#define FS_LAUNCH_RELAX(MODE_, HZ_, PUSH_, NZ_, BASE_, STRIDE_) \
+            cudaStream_t ls = st;                                  // stream of the next launch
+            int kl_b = kl0, kl_e = kl0 + cnt, kl_alt = 0, zc = 1;  // plane range / chunk length of the next launch
+#define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
-         launch_on(st, relax_vec4<MODE_, HZ_, PUSH_>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, push, kl_alt); } while (0)
-#define FS_LAUNCH_RELAX_MODE(PUSH_, NZ_, BASE_, STRIDE_) \
-    do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, false, NZ_, BASE_, STRIDE_); } \
-         else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, PUSH_, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, false, NZ_, BASE_, STRIDE_); } } while (0)
-            const bool exchange = halo_on && fuse_halo;
-            if (exchange && fused_push) {
-                // The boundary-chunk launch pushes its own planes (relax_vec4<.., PUSH = true>): wait for the neighbours'
-                // previous op, compute, store local + remote, publish.  One halo operation, no push kernel.
-                push.op_offset = ++ops_since_commit;
-                push.my_flags = my_flags;
-                push.kb = g.kb; push.ke = g.ke;
-                {   // chunks of the launch that will push, and how many of them touch each side's FS_GHOST boundary planes
-                    const int zsp = push_planes > FS_GHOST ? push_planes : FS_GHOST;
-                    const bool split = cnt >= 3 * zsp + 2;
-                    int n_lo = 0, n_hi = 0;
-                    if (split) { n_lo = n_hi = 1; }
-                    else
-                        for (int q = 0; q < nchunks; q++) {
-                            const int lo_pl = kl0 + q * (int)zchunk, hi_pl = std::min(lo_pl + (int)zchunk, kl0 + cnt);
-                            if (lo_pl < g.kb + FS_GHOST) n_lo++;
-                            if (hi_pl > g.ke - FS_GHOST) n_hi++;
-                        }
-                    push.side_ctas_lo = (unsigned)(gxn * gyn * nf * n_lo);
-                    push.side_ctas_hi = (unsigned)(gxn * gyn * nf * n_hi);
-                }
-                if (lo.present) push.lo_flags = lo.flags;
-                if (hi.present) push.hi_flags = hi.flags;
-                for (int f = 0; f < nf; f++) {
-                    const int bi = buf_index(out[f]);
-                    if (lo.present && bi >= 0) push.lo_dst[f] = lo.base[bi] + g.sz * (lo.nzl - FS_GHOST);
-                    if (hi.present && bi >= 0) push.hi_dst[f] = hi.base[bi];
-                }
-                pending_incoming = true;                       // nobody has waited for the neighbours' planes of this op yet
-                // The pushing instantiation is the slower one (118 registers, 2 CTAs/SM): give it as few planes as the
-                // exchange needs -- two thin chunks of zs planes at the slab's ends -- and everything between to the hot kernel.
-                const int zs = push_planes > FS_GHOST ? push_planes : FS_GHOST;
-                if (cnt >= 3 * zs + 2) {
-                    FS_CUDA(cudaEventRecord(ev_fork, st));
-                    FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
-                    { cudaStream_t main_st = st; st = st_halo;
-                      kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - zs; zc = zs;
-                      FS_LAUNCH_RELAX_MODE(true, 2, 0, 0);          // [kl0, kl0+zs) and [kl0+cnt-zs, kl0+cnt), pushing
-                      st = main_st; }
-                    FS_CUDA(cudaEventRecord(ev_join, st_halo));
-                    kl_b = kl0 + zs; kl_e = kl0 + cnt - zs;
-                    long long zi = (long long)(cnt - 2 * zs) * blocks_xy * nf / target;
-                    zi = zi < 4 ? 4 : (zi > 16 ? 16 : zi);
-                    if (tune_zchunk > 0) zi = tune_zchunk;
-                    if (zi > cnt - 2 * zs) zi = cnt - 2 * zs;
-                    zc = (int)zi;
-                    const int ni = (int)((cnt - 2 * zs + zi - 1) / zi);
-                    FS_LAUNCH_RELAX_MODE(false, ni, 0, 1);           // everything between, concurrently
-                    FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-                } else {
-                    FS_LAUNCH_RELAX_MODE(true, nchunks, 0, 1);
-                }
-            } else if (exchange && (exchange_mode == 1 || (exchange_mode == 2 && cnt <= serial_max_planes)) && cnt >= 3 * FS_GHOST * 2 + 2) {
-                // serial schedule, one stream: the boundary planes first (two thin chunks), their push without trailing wait,
-                // then everything between; the wait for the neighbours' planes is issued before the NEXT reader of the ghosts
-                const int zs = 2 * FS_GHOST;
-                halo_wait_pending();
-                kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - zs; zc = zs;
-                FS_LAUNCH_RELAX_MODE(false, 2, 0, 0);
-                halo_n_on_stream(g, out, nf, st, /*wait_incoming=*/false);
-                kl_b = kl0 + zs; kl_e = kl0 + cnt - zs;
-                long long zi = (long long)(cnt - 2 * zs) * blocks_xy * nf / target;
-                zi = zi < 4 ? 4 : (zi > 16 ? 16 : zi);
-                if (tune_zchunk > 0) zi = tune_zchunk;
-                if (zi > cnt - 2 * zs) zi = cnt - 2 * zs;
-                zc = (int)zi;
-                FS_LAUNCH_RELAX_MODE(false, (int)((cnt - 2 * zs + zi - 1) / zi), 0, 1);
-            } else if (exchange && nchunks > 2) {
-                // fork: side stream = boundary chunks, then the P2P push kernel; main stream = interior chunks; join
+         launch_on(ls, relax_vec4<MODE_, HZ_>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, kl_alt); } while (0)
+#define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
+    do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
+         else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
+            // the whole range [kl0, kl0+cnt) as one launch on stream ls
+            auto launch_all = [&]() {
+                kl_b = kl0; kl_e = kl0 + cnt; zc = chunk_for(cnt);
+                FS_LAUNCH_RELAX_MODE((cnt + zc - 1) / zc, 0, 1);
+            };
+            // [kl0, kl0+ends) and [kl0+cnt-ends, kl0+cnt) as one two-chunk launch; everything between as another
+            auto launch_ends = [&](int ends) {
+                kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - ends; zc = ends;
+                FS_LAUNCH_RELAX_MODE(2, 0, 0);
+            };
+            auto launch_middle = [&](int ends) {
+                const int mid = cnt - 2 * ends;
+                kl_b = kl0 + ends; kl_e = kl0 + cnt - ends; zc = chunk_for(mid);
+                FS_LAUNCH_RELAX_MODE((mid + zc - 1) / zc, 0, 1);
+            };
+            const int be = 4, ee = 3; // planes per end of an exchange sweep's / an extended sweep's boundary launch (see below)
+            if (exchange && cnt >= 2 * be + 4) {
+                // fork: side stream = the two ends of the slab, then the P2P push kernel (stores them into the neighbours'
+                // ghosts, signals, awaits theirs); main stream = everything between, concurrently; join
+                if (fork_open) join_fork();                        // (callers pair OPEN with EXTEND; defensive)
                 FS_CUDA(cudaEventRecord(ev_fork, st));
                 FS_CUDA(cudaStreamWaitEvent(st_halo, ev_fork, 0));
-                { cudaStream_t main_st = st; st = st_halo;
-                  FS_LAUNCH_RELAX_MODE(false, 2, 0, nchunks - 1);
-                  st = main_st; }
-                halo_n_on_stream(g, out, nf, st_halo);         // stores them into the neighbours' ghosts, signals, awaits theirs
-                FS_CUDA(cudaEventRecord(ev_join, st_halo));
-                FS_LAUNCH_RELAX_MODE(false, nchunks - 2, 1, 1);
-                FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // join (also required before a graph capture ends)
+                ls = st_halo;
+                launch_ends(be);
+                FS_CUDA(cudaEventRecord(ev_ends, st_halo));
+                halo_n_on_stream(g, out, nf, st_halo);
+                ls = st;
+                launch_middle(be);
+                if (xmode == FS_X_EXCHANGE_OPEN) fork_open = true;
+                else join_fork();
+            } else if (extend && fork_open && cnt >= 2 * ee + 4) {
+                // The previous sweep's fork is still open: its push (side stream) may be in flight.  Only the ends of THIS
+                // sweep read ghost planes, so they follow the push on the side stream, while the middle starts as soon as
+                // the previous sweep's ends are done.  Data flow: the ends ([kl0, kl0+3) and its mirror image) read the
+                // previous output on planes kl0-1 .. kl0+3, all of which the previous sweep's 4-plane ends or the push wrote
+                // (same stream); they overwrite planes <= kl0+2 of the previous INPUT buffer, which the previous middle
+                // launch (planes >= kl0+be, reading from kl0+be-1 = kl0+3 at the owned range; one less here) no longer reads.
+                ls = st_halo;
+                launch_ends(ee);
+                halo_ack_on_stream(st_halo);
+                ls = st;
+                FS_CUDA(cudaStreamWaitEvent(st, ev_ends, 0));
+                launch_middle(ee);
+                join_fork();
             } else {
-                FS_LAUNCH_RELAX_MODE(false, nchunks, 0, 1);
+                if (fork_open) join_fork();
+                launch_all();
                 if (exchange) halo_n_on_stream(g, out, nf, st);
+                if (extend) halo_ack_on_stream(st);
             }
 #undef FS_LAUNCH_RELAX_MODE
 #undef FS_LAUNCH_RELAX
             return;
         }
+        if (fork_open) join_fork();
         for (int f = 0; f < nf; f++) {
             const float *in_f = in[f], *rhs_f = rhs ? rhs[f] : nullptr, *stale_f = stale ? stale[f] : nullptr;
             float *out_f = out[f];
             const int b_f = b[f];
             if (mode == FS_MODE_SMOOTH)
-                cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
+                cells_range(g, kl0, cnt, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
             else
-                cells(g, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
+                cells_range(g, kl0, cnt, [=] __device__(int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in_f, rhs_f, stale_f, out_f, flags, a, c, b_f, in_zero, i, j, kl); });
         }
-        if (fuse_halo) halo_n_on_stream(g, out, nf, st); // per-cell fallback: push after the whole sweep
+        if (exchange) halo_n_on_stream(g, out, nf, st); // per-cell fallback: push after the whole sweep
+        if (extend) halo_ack_on_stream(st);
     }
-    // After a run of sweeps whose push is fused into the boundary launch nobody has yet waited for the neighbours' planes
-    // of the LAST sweep: a fence (its own tiny halo op) does, before a kernel that is not a sweep reads the ghost planes.
-    bool fused_push = false;      // FS_FUSED_PUSH=1: the boundary launch pushes its own planes (measured slower, profiles/r02e_exchange.md)
-    int push_planes = 4;          // FS_PUSH_PLANES: planes per end given to the pushing instantiation
-    bool pending_incoming = false;
+    bool extend_sweeps = true;    // FS_EXTEND=0: every sweep exchanges (one halo operation per sweep)
+    bool fork_open = false;       // an FS_X_EXCHANGE_OPEN sweep has left the side stream un-joined
+    void join_fork() {
+        FS_CUDA(cudaEventRecord(ev_join, st_halo));
+        FS_CUDA(cudaStreamWaitEvent(st, ev_join, 0));  // (also required before a graph capture ends)
+        fork_open = false;
+    }
+    // end of a run of sweeps: nothing may stay forked
     void relax_end() {
-        if (halo_on && pending_incoming) halo_fence();
-        pending_incoming = false;
-        halo_wait_pending();
+        if (fork_open) join_fork();
     }
-    // Exchange schedule of a sweep on z-slabs (FS_EXCHANGE): 0 fork/join (boundary chunks + push on a side stream beside the
-    // interior launch), 1 serial (one stream: [wait for the previous sweep's incoming planes] -> thin boundary launch ->
-    // push without trailing wait -> interior launch; the neighbours' planes arrive while the interior runs), 2 auto = serial
-    // for thin slabs.  profiles/r02e_exchange.md has the measurements.
-    int exchange_mode = 2;
-    int serial_max_planes = 96;
     // Fused two-stage sweep (fs_kernels.cuh relax_pair): out = S2(S1(in)).  Returns false when this grid / field
     // cannot take it (the caller then issues two single sweeps): 2D, nx % 4 != 0, unusable divisor, FS_NO_PAIR.
     // Policy (FS_PAIR = 0 never / 1 always / unset: auto).  Measured on B200 (profiles/r02b_pair_kernel.md): the fused
@@ -900,26 +885,27 @@ struct CudaExec {
         halo_n_on_stream(g, fields, field ? 1 : 0, stream);
     }
     void halo_n(const FsGrid &g, float *const *fields, int nf) { halo_n_on_stream(g, fields, nf, st); }
-    void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream, bool wait_incoming = true) {
+    void halo_n_on_stream(const FsGrid &g, float *const *fields, int nf, cudaStream_t stream) {
         if (!halo_on) return;
-        // a standalone op starts by waiting for the neighbours' previous op: whatever was left open is closed by it
-        pending_incoming = false;
-        pending_wait_op = 0;
         const unsigned op = ++ops_since_commit;
-        const FsHaloArgs h = halo_args(g, fields, nf, op);
+        FsHaloArgs h = halo_args(g, fields, nf, op);
+        h.need_ack = ack_since_last_op ? 1 : 0;
+        ack_since_last_op = false;
         const long long plane = g.sz * FS_GHOST;
         int blocks = (int)((plane / 4 + 255) / 256) * (nf > 1 ? nf : 1);
         if (blocks > sm_count * 2) blocks = sm_count * 2;
         if (blocks < 1 || nf == 0) blocks = 1;
-        launch_on(stream, halo_push_kernel, dim3(blocks), dim3(256), h, nf ? plane : 0LL, wait_incoming ? 1 : 0);
-        if (!wait_incoming) pending_wait_op = op;
+        launch_on(stream, halo_push_kernel, dim3(blocks), dim3(256), h, nf ? plane : 0LL);
     }
-    // closes a push that did not wait for the neighbours' planes (serial exchange schedule)
-    unsigned pending_wait_op = 0;
-    void halo_wait_pending() {
-        if (!halo_on || !pending_wait_op) return;
-        launch_on(st, halo_wait_kernel, dim3(1), dim3(32), my_flags, lo.present ? 1 : 0, hi.present ? 1 : 0, pending_wait_op);
-        pending_wait_op = 0;
+    // After an FS_X_EXTEND sweep (which read ghost planes WITHOUT a halo operation of its own): tell the neighbours that the
+    // ghost planes their last push filled have been consumed.  Their next push -- the first operation that overwrites
+    // those planes -- waits for this (FsHaloArgs::need_ack), see the protocol notes in fs_kernels.cuh.
+    bool ack_since_last_op = false;
+    void halo_ack_on_stream(cudaStream_t stream) {
+        if (!halo_on) return;
+        launch_on(stream, halo_ack_kernel, dim3(1), dim3(32), my_flags, lo.present ? lo.flags : nullptr,
+                  hi.present ? hi.flags : nullptr, ops_since_commit);
+        ack_since_last_op = true;
     }
     void halo_fence() { // neighbours have finished everything enqueued before this point, and vice versa
         if (!halo_on) return;

@@ -154,6 +154,7 @@ int fs_op_lin_solve(fs_solver *s, int32_t dst, int32_t rhs, int32_t b, float a, 
     float **d = c.field_slot(dst);
     float *r = c.field_ptr(rhs);
     if (!d || !*d || !r || dst == rhs || !fs_valid_b(c, b) || iters < 0) return c.fail(FS_ERR_BAD_ARGUMENT, "bad argument");
+    c.ex.halo(c.g, r); // slabs: fused / extended sweeps read the right-hand side one plane into the ghost zone
     if (solver_kind == FS_RED_BLACK)
         c.lin_solve_rb(b, *d, r, a, cc, iters, false);
     else

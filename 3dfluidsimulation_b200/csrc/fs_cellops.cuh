@@ -33,9 +33,12 @@ enum { FS_MODE_SMOOTH = 0, FS_MODE_JACOBI = 1 };
 // fused two-stage sweeps (fs_kernels.cuh relax_pair): two smoother / Jacobi iterations, or the two colour passes of one
 // red-black sweep, per pass over HBM
 enum { FS_PAIR_SMOOTH = 0, FS_PAIR_JACOBI = 1, FS_PAIR_RED_BLACK = 2 };
+// how a single sweep on z-slabs relates to the halo exchange (executor relax / relax_n; 0 / 1 also read as false / true)
+enum { FS_X_NONE = 0, FS_X_EXCHANGE = 1, FS_X_EXTEND = 2, FS_X_EXCHANGE_OPEN = 3 };
 
-// Ghost planes per internal slab side.  Two: a fused two-stage sweep evaluates its first stage one plane beyond the
-// owned range, which reads one plane further; every halo operation moves FS_GHOST planes each way.
+// Ghost planes per internal slab side.  Two: an extended sweep (FS_X_EXTEND) or the first stage of a fused two-stage
+// sweep is evaluated one plane beyond the owned range, which reads one plane further; every halo operation moves
+// FS_GHOST planes each way, so two sweeps can share one operation.
 #define FS_GHOST 2
 
 // Geometry of one z-slab.  Local arrays hold planes [zoff, zoff+nzl) of the global grid; the slab

@@ -216,8 +216,17 @@ struct SolverCore {
     // components, the obstacle mirroring (fs_mirror_fused recomputes the two neighbour values it needs).  On z-slabs the
     // executor overlaps the push of the boundary planes with the interior of the same sweep.
     void relax_op(int mode, const float *in, const float *rhs, const float *stale, float *out, float a, float c, int b,
-                  bool in_zero) {
-        ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, /*fuse_halo=*/true);
+                  bool in_zero, int xmode) {
+        ex.relax(mode, g, in, rhs, stale, out, fl(), a, c, b, in_zero, xmode);
+    }
+    // z-slabs: sweeps without obstacle mirroring go in twos per halo operation (the ghost zone is two planes deep): sweep
+    // `it` of `iters` is an extended one when another sweep follows it, the exchanging one after it leaves its fork open
+    // when a further couple follows.  Every rank takes the same decisions (they only depend on global facts).
+    bool extendable(int b) const { return ex.can_extend(g) && !needs_mirror(b); }
+    static int sweep_xmode(bool ext, int it, int iters) {
+        if (!ext) return FS_X_EXCHANGE;
+        if ((it & 1) == 0) return it + 1 < iters ? FS_X_EXTEND : FS_X_EXCHANGE;
+        return it + 2 < iters ? FS_X_EXCHANGE_OPEN : FS_X_EXCHANGE;
     }
     // Whether sweeps of field kind b may be fused in pairs: no obstacle mirroring between the two stages.
     bool needs_mirror(int b) const { return b != 0 && g_interior_obstacle && (b != 3 || g.hz); }
@@ -233,13 +242,14 @@ struct SolverCore {
         // they hold x0 throughout, so `stale = x0` is exact for every iteration.  With mirroring (b != 0 and interior
         // obstacles) the stale content is the mirrored value of two iterations ago: x0 for the first two, then the buffer.
         const bool mir = needs_mirror(b);
+        const bool ext = !pairs && extendable(b);
         int sweeps = 0;
         for (int it = 0; it < iters;) {
             float *out = (sweeps & 1) ? B : A;
             if (pairs && it + 2 <= iters && ex.relax_pair(FS_PAIR_SMOOTH, g, in, nullptr, out, fl(), a, c, b, false, true)) {
                 it += 2;
             } else {
-                relax_op(FS_MODE_SMOOTH, in, nullptr, (!mir || it < 2) ? x0 : nullptr, out, a, c, b, false);
+                relax_op(FS_MODE_SMOOTH, in, nullptr, (!mir || it < 2) ? x0 : nullptr, out, a, c, b, false, sweep_xmode(ext, it, iters));
                 it += 1;
             }
             in = out;
@@ -255,12 +265,13 @@ struct SolverCore {
         if (iters == 0) { if (zero_guess) ex.zero(x, sizeof(float) * nloc); return; }
         float *rd = x, *wr = tmp;
         const bool pairs = pair_ok(b, c, FS_PAIR_JACOBI);
+        const bool ext = !pairs && extendable(b); // (the right-hand side must then be valid one plane into the ghost zone)
         for (int it = 0; it < iters;) {
             const bool iz = zero_guess && it == 0;
             if (pairs && it + 2 <= iters && ex.relax_pair(FS_PAIR_JACOBI, g, rd, rhs, wr, fl(), a, c, b, iz, true)) {
                 it += 2;
             } else {
-                relax_op(FS_MODE_JACOBI, rd, rhs, nullptr, wr, a, c, b, iz);
+                relax_op(FS_MODE_JACOBI, rd, rhs, nullptr, wr, a, c, b, iz, sweep_xmode(ext, it, iters));
                 it += 1;
             }
             std::swap(rd, wr);
@@ -320,12 +331,13 @@ struct SolverCore {
         const float *in[3] = {x0[0], x0[1], x0[2]}, *stale[3];
         float *out[3], *A[3], *B[3];
         for (int f = 0; f < nf; f++) { A[f] = *scratch[f]; B[f] = *x[f]; }
+        const bool ext = extendable(1); // (needs_mirror is the same for every component that exists)
         for (int it = 0; it < iters; it++) {
             for (int f = 0; f < nf; f++) {
                 out[f] = (it & 1) ? B[f] : A[f];
                 stale[f] = (!needs_mirror(b[f]) || it < 2) ? x0[f] : nullptr; // see smooth()
             }
-            ex.relax_n(FS_MODE_SMOOTH, g, nf, in, nullptr, stale, out, fl(), a, c, b, false, true);
+            ex.relax_n(FS_MODE_SMOOTH, g, nf, in, nullptr, stale, out, fl(), a, c, b, false, sweep_xmode(ext, it, iters));
             for (int f = 0; f < nf; f++) in[f] = out[f];
         }
         // pass 2 (LinearSolveWithJobs) seeded with pass 1's result, rhs = x0
@@ -333,7 +345,7 @@ struct SolverCore {
         for (int f = 0; f < nf; f++) { rd[f] = const_cast<float *>(in[f]); wr[f] = rd[f] == A[f] ? B[f] : A[f]; }
         for (int it = 0; it < iters; it++) {
             const float *rdc[3] = {rd[0], rd[1], rd[2]};
-            ex.relax_n(FS_MODE_JACOBI, g, nf, rdc, x0, nullptr, wr, fl(), a, c, b, false, true);
+            ex.relax_n(FS_MODE_JACOBI, g, nf, rdc, x0, nullptr, wr, fl(), a, c, b, false, sweep_xmode(ext, it, iters));
             for (int f = 0; f < nf; f++) std::swap(rd[f], wr[f]);
         }
         ex.relax_end();
@@ -349,9 +361,11 @@ struct SolverCore {
     // ---- ProjectWithJobs (FluidSim.cs:1417-1521) ------------------------------------------------
     void project(float *ux, float *uy, float *uz) {
         ex.divergence(g, div, ux, uy, uz);
-        // slabs + fused sweeps: the first stage is evaluated one plane into the ghost zone and reads the right-hand
-        // side there (a single sweep only reads div on owned planes)
-        if (pair_ok(0, 6.0f, prm.solver_kind == FS_RED_BLACK ? FS_PAIR_RED_BLACK : FS_PAIR_JACOBI)) ex.halo(g, div);
+        // slabs + fused or extended sweeps: those are evaluated one plane into the ghost zone and read the right-hand
+        // side there (a plain single sweep only reads div on owned planes)
+        if (pair_ok(0, 6.0f, prm.solver_kind == FS_RED_BLACK ? FS_PAIR_RED_BLACK : FS_PAIR_JACOBI) ||
+            (prm.solver_kind != FS_RED_BLACK && extendable(0)))
+            ex.halo(g, div);
         if (prm.solver_kind == FS_RED_BLACK)
             lin_solve_rb(0, pressure, div, 1.0f, 6.0f, prm.iters_pressure, true);
         else

@@ -130,12 +130,19 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 //     are only read by kernels ordered BEFORE the neighbour's previous signal, or carry identical values.
 // An in-place op followed by a halo of a field whose ghost a neighbour kernel may still be reading would race; such
 // an op needs a halo_fence() (consumer-done) first.
-// For the relaxation sweeps a slab forks: side stream = boundary-chunk launch of relax_vec4 -> halo_push_kernel
-// (wait seq-1, store, signal seq, wait for the incoming seq); main stream = interior-chunk launch; join.  The two
-// launches run concurrently, so the exchange is hidden behind the interior chunks.  (Fusing the three steps INTO relax_vec4 was built and measured: any
-// form of it -- inlined or as noinline device functions -- cost the 64-register sweep 20-30% through register
-// pressure / lost uniform registers, see profiles/r01d_halo_variants.md, so the sweep kernel stays untouched.)
-enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_CNT_HI = 4, FS_HF_ERROR = 5, FS_HF_WORDS = 8 };
+//   * extended sweeps (FS_X_EXTEND: two sweeps per operation -- the first also computes the first ghost plane from the
+//     two-deep ghost zone, the second exchanges) read ghost planes in a kernel that belongs to NO operation, and the very
+//     next operation overwrites them (same ping-pong buffer).  Here the discipline above does not hold, so the consumer
+//     says so explicitly: halo_ack_kernel stores seq into the neighbours' ACK words once the reading launch is complete,
+//     and the next push (FsHaloArgs::need_ack) also waits for ACK >= seq-1 before it stores.
+// Schedule of the relaxation sweeps on a slab (CudaExec::relax_n): side stream = the two ends of the slab (a two-chunk
+// launch of relax_vec4) -> halo_push_kernel (wait seq-1, store, signal seq, wait for the incoming seq); main stream = the
+// planes between, concurrently; join.  With extended sweeps the join is deferred: only the ENDS of the extended sweep
+// (side stream, after the push) read ghost planes, its middle starts as soon as the previous sweep's ends are done, so
+// one exchange hides behind two interior launches.  (Fusing wait / store / signal INTO relax_vec4 was built twice --
+// round 1 inlined, round 2 as a separate instantiation for the ends -- and measured slower both times: register
+// pressure in the 64-register sweep, profiles/r01d_halo_variants.md, profiles/r02e_exchange.md.)
+enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_ERROR = 5, FS_HF_ACK_FROM_LO = 6, FS_HF_ACK_FROM_HI = 7, FS_HF_WORDS = 8 };
 
 #define FS_BATCH 3 // fields per batched launch / halo operation (the velocity components)
 struct FsHaloArgs {
@@ -148,6 +155,7 @@ struct FsHaloArgs {
     unsigned *lo_flags;              // neighbours' flag blocks (peer memory)
     unsigned *hi_flags;
     unsigned op_offset;
+    int need_ack;                    // an extended sweep read the ghost planes since the last operation: wait for the neighbours' acknowledgement too
     unsigned long long *trace;       // optional (FS_HALO_TRACE): 4 %globaltimer stamps per operation, ring of trace_cap entries
     unsigned trace_cap;
 };
@@ -189,7 +197,7 @@ __device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
 // Copies the FS_GHOST boundary planes of up to FS_BATCH fields into the neighbours' ghost planes (nf = 0: pure fence)
 // after waiting for seq-1, then signals seq and waits for the neighbours' seq.  plane_elems = FS_GHOST*nx*ny.
 __global__ void __launch_bounds__(256)
-halo_push_kernel(const FsHaloArgs h, long long plane_elems, const int wait_incoming) {
+halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
     __shared__ unsigned s_seq;
     if (threadIdx.x == 0) {
         const unsigned seq = halo_seq(h);
@@ -197,6 +205,10 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems, const int wait_incom
         if (tr) tr[0] = fs_globaltimer_ns();             // kernel start
         if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
         if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
+        if (h.need_ack) { // ... and they have finished reading the ghost planes that operation filled (extended sweeps)
+            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_ACK_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
+            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_ACK_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
+        }
         if (tr) tr[1] = fs_globaltimer_ns();             // neighbours' previous operation seen
         s_seq = seq;
     }
@@ -228,24 +240,22 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems, const int wait_incom
             if (h.hi_flags) st_release_sys(h.hi_flags + FS_HF_FROM_LO, s_seq);
             // ... and do not retire before the neighbours' planes of the same op have landed here: whatever
             // is ordered after this kernel may read the ghost planes (no separate wait launch needed)
-            if (wait_incoming) {
-                if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
-                if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
-            }
-            if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed (or: not awaited here)
+            if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, s_seq, h.my_flags + FS_HF_ERROR);
+            if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, s_seq, h.my_flags + FS_HF_ERROR);
+            if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed
         }
     }
 }
 
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
 
-// The wait a push without trailing wait leaves open: returns once both neighbours have published operation
-// base + op_offset, i.e. their planes of that operation have landed in this slab's ghost planes.
-__global__ void halo_wait_kernel(unsigned *my_flags, const int has_lo, const int has_hi, const unsigned op_offset) {
+// Published after an extended sweep (one that read ghost planes without a halo operation of its own): "I have consumed
+// the ghost planes your operation base + op_offset filled".  The neighbours' next push waits for it.
+__global__ void halo_ack_kernel(const unsigned *my_flags, unsigned *lo_flags, unsigned *hi_flags, const unsigned op_offset) {
     if (threadIdx.x == 0) {
         const unsigned seq = *(volatile const unsigned *)(my_flags + FS_HF_BASE) + op_offset;
-        if (has_lo) halo_spin_until(my_flags + FS_HF_FROM_LO, seq, my_flags + FS_HF_ERROR);
-        if (has_hi) halo_spin_until(my_flags + FS_HF_FROM_HI, seq, my_flags + FS_HF_ERROR);
+        if (lo_flags) st_release_sys(lo_flags + FS_HF_ACK_FROM_HI, seq);
+        if (hi_flags) st_release_sys(hi_flags + FS_HF_ACK_FROM_LO, seq);
     }
 }
 
@@ -324,27 +334,11 @@ tilemap_scan_kernel(int *cum, int ntiles, int nzl) {
         cum[(long long)kl * ntiles + t] = count;
     }
 }
-// Halo push fused into the boundary-chunk launch of a sweep (PUSH = true instantiation, z-slabs only).  The CTAs of the first
-// and last z chunk wait for the neighbour's previous operation before they read the ghost planes, store every float4 they
-// write into the FS_GHOST boundary planes to the neighbour's ghost planes as well (P2P), and the last CTA of a side to
-// finish publishes the operation's sequence number in the neighbour's flag word.  No separate push kernel, so nothing
-// of the exchange has to squeeze in between the interior CTAs (trace at N = 8, 512^3: the standalone push kernel needed
-// 13 us for 4 MB while the interior launch held the SMs, 22 us in all per sweep on the critical path); the interior
-// launch (PUSH = false, the untouched hot kernel) runs beside it.  The incoming planes are awaited by whoever reads them
-// next: the next sweep's boundary CTAs, or the fence the executor issues after a run of sweeps.
-struct FsPushArgs {
-    float *lo_dst[FS_BATCH];         // lower neighbour's top ghost planes of each output field (my plane kb lands on their first)
-    float *hi_dst[FS_BATCH];         // upper neighbour's bottom ghost planes (my plane ke - FS_GHOST lands on their plane 0)
-    unsigned *my_flags, *lo_flags, *hi_flags;
-    unsigned op_offset;
-    int kb, ke;                      // owned local planes [kb, ke)
-    unsigned side_ctas_lo, side_ctas_hi; // CTAs (all fields) whose planes touch the lower / upper boundary planes: the counts that complete a side
-};
-template <int MODE, bool HZ, bool PUSH>
-__global__ void __launch_bounds__(256, PUSH ? 2 : 4)
+template <int MODE, bool HZ>
+__global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
            const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
-           const int zc_stride, const int l2_ahead, const FsPushArgs push, const int kl_alt) {
+           const int zc_stride, const int l2_ahead, const int kl_alt) {
     const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
     const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
     const float *__restrict__ in = fld == 0 ? batch.in[0] : (fld == 1 ? batch.in[1] : batch.in[2]);
@@ -359,30 +353,11 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     // sweep is issued as two launches of this same kernel -- the two chunks that hold the slab's boundary planes
     // first (base 0, stride nchunks-1), then the interior chunks (base 1, stride 1) -- with the P2P halo push
     // between them, so the exchange overlaps the interior (fluidsolver.cu, CudaExec::relax).
-    // (zc_stride == 0: the two-chunk boundary launch of the fused push -- chunk 0 starts at kl_begin, chunk 1 at kl_alt)
+    // (zc_stride == 0: a two-chunk launch for the two ends of a slab -- chunk 0 starts at kl_begin, chunk 1 at kl_alt)
     const int zc = zc_base + zblk * zc_stride;
     const int k_lo = zc_stride == 0 ? (zblk == 0 ? kl_begin : kl_alt) : kl_begin + zc * zchunk;
     const int k_hi = min(k_lo + zchunk, kl_end);
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
-    // PUSH: which sides this CTA's planes touch, peer offsets of this field, and the wait for the neighbours' previous op
-    const bool side_lo = PUSH && push.lo_flags && k_lo < k_hi && k_lo < push.kb + FS_GHOST;
-    const bool side_hi = PUSH && push.hi_flags && k_lo < k_hi && k_hi > push.ke - FS_GHOST;
-    long long dlo = 0, dhi = 0;
-    __shared__ unsigned s_push_seq;
-    if (PUSH) {
-        float *lo_dst = fld == 0 ? push.lo_dst[0] : (fld == 1 ? push.lo_dst[1] : push.lo_dst[2]);
-        float *hi_dst = fld == 0 ? push.hi_dst[0] : (fld == 1 ? push.hi_dst[1] : push.hi_dst[2]);
-        // element offset from a cell of my boundary planes to the same cell of the neighbour's ghost planes
-        dlo = ((long long)(size_t)lo_dst - (long long)(size_t)(out + g.sz * push.kb)) / (long long)sizeof(float);
-        dhi = ((long long)(size_t)hi_dst - (long long)(size_t)(out + g.sz * (push.ke - FS_GHOST))) / (long long)sizeof(float);
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            const unsigned seq = *(volatile const unsigned *)(push.my_flags + FS_HF_BASE) + push.op_offset;
-            if (side_lo) halo_spin_until(push.my_flags + FS_HF_FROM_LO, seq - 1, push.my_flags + FS_HF_ERROR);
-            if (side_hi) halo_spin_until(push.my_flags + FS_HF_FROM_HI, seq - 1, push.my_flags + FS_HF_ERROR);
-            s_push_seq = seq;
-        }
-        __syncthreads();
-    }
     if (active) {
     const FsDivisor dv = fs_make_divisor(c);
     const bool first_x = x0 == 0, last_x = x0 + 4 == g.nx;
@@ -462,10 +437,6 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
             if (first_x) v[0] = b == 1 ? -v[1] : v[1];
             if (last_x) v[3] = b == 1 ? -v[2] : v[2];
             st4(pout, v);
-            if (PUSH) {
-                if (side_lo && kl < push.kb + FS_GHOST) st4(pout + dlo, v);
-                if (side_hi && kl >= push.ke - FS_GHOST) st4(pout + dhi, v);
-            }
         } else {
             // ring lanes take their nearest interior lane's value; fs_ring_value applies the face rules
             if (first_x) v[0] = v[1];
@@ -484,10 +455,6 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
                     for (int l = 0; l < 4; l++) o[l] = fs_ring_value(v[l], fxl[l], fys[yi], fzs[zi], b);
                     float *po = out + fs_idx(g, x0, ys[yi], zs[zi]);
                     st4(po, o);
-                    if (PUSH && zi == 0) { // (the z ring planes are global boundary planes: never part of an exchange)
-                        if (side_lo && kl < push.kb + FS_GHOST) st4(po + dlo, o);
-                        if (side_hi && kl >= push.ke - FS_GHOST) st4(po + dhi, o);
-                    }
                 }
             }
         }
@@ -499,12 +466,7 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
 #pragma unroll
                 for (int l = 0; l < 4; l++) {
                     if (!((fl >> (8 * l)) & 1u) || (l == 0 && first_x) || (l == 3 && last_x)) continue;
-                    const float mv = fs_mirror_fused<MODE>(g, in, rhs, (uint8_t)(fl >> (8 * l)), a, c, b, in_zero != 0, v[l], x0 + l, j, kl);
-                    pout[l] = mv;
-                    if (PUSH) {
-                        if (side_lo && kl < push.kb + FS_GHOST) pout[l + dlo] = mv;
-                        if (side_hi && kl >= push.ke - FS_GHOST) pout[l + dhi] = mv;
-                    }
+                    pout[l] = fs_mirror_fused<MODE>(g, in, rhs, (uint8_t)(fl >> (8 * l)), a, c, b, in_zero != 0, v[l], x0 + l, j, kl);
                 }
             }
         }
@@ -512,22 +474,6 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
         cur = next;
     }
     } // active
-    if (PUSH) { // publish: every store of this CTA is fenced, the last CTA of a side signals the neighbour
-        if (side_lo || side_hi) __threadfence_system();
-        __syncthreads();
-        if (threadIdx.x == 0 && threadIdx.y == 0) {
-            if (side_lo && atomicAdd(push.my_flags + FS_HF_CNT_LO, 1u) == push.side_ctas_lo - 1) {
-                push.my_flags[FS_HF_CNT_LO] = 0;
-                __threadfence_system();
-                st_release_sys(push.lo_flags + FS_HF_FROM_HI, s_push_seq);
-            }
-            if (side_hi && atomicAdd(push.my_flags + FS_HF_CNT_HI, 1u) == push.side_ctas_hi - 1) {
-                push.my_flags[FS_HF_CNT_HI] = 0;
-                __threadfence_system();
-                st_release_sys(push.hi_flags + FS_HF_FROM_LO, s_push_seq);
-            }
-        }
-    }
 }
 
 // ---- float4 versions of the once-per-step stencils --------------------------------------------------------

@@ -56,19 +56,36 @@ struct HostExec {
         launches++;
     }
 
+    // xmode: FS_X_* (fs_cellops.cuh).  An extended sweep also computes the first ghost plane on each side that has a
+    // neighbour, from local data only, and acknowledges the ghost planes it read (see halo()).
+    bool can_extend(const FsGrid &g) const {
+        const char *e = getenv("FS_EXTEND");
+        return halo_on && g.hz && !(e && e[0] == '0');
+    }
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
-               const uint8_t *flags, float a, float c, int b, bool in_zero, bool fuse_halo) {
+               const uint8_t *flags, float a, float c, int b, bool in_zero, int xmode) {
+        const int zb = g.zoff + g.kb, ze = g.zoff + g.ke;
+        int k0 = g.hz ? (zb < 1 ? 1 : zb) - g.zoff : 0, k1 = g.hz ? (ze > g.nz - 1 ? g.nz - 1 : ze) - g.zoff : 1;
+        const bool extend = halo_on && xmode == FS_X_EXTEND;
+        if (extend) {
+            if (lo.present) k0 -= 1;
+            if (hi.present) k1 += 1;
+        }
         if (mode == FS_MODE_SMOOTH)
-            cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+            cells_range(g, k0, k1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_SMOOTH>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
         else
-            cells(g, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
-        if (fuse_halo) halo(g, out);
+            cells_range(g, k0, k1, [&](int i, int j, int kl) { fs_relax_cell<FS_MODE_JACOBI>(g, in, rhs, stale, out, flags, a, c, b, in_zero, i, j, kl); });
+        launches++;
+        if (xmode == FS_X_EXCHANGE || xmode == FS_X_EXCHANGE_OPEN) halo(g, out);
+        if (extend) ack();
     }
     void relax_n(int mode, const FsGrid &g, int nf, const float *const *in, const float *const *rhs, const float *const *stale,
-                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, bool fuse_halo) {
+                 float *const *out, const uint8_t *flags, float a, float c, const int *b, bool in_zero, int xmode) {
+        const bool exch = xmode == FS_X_EXCHANGE || xmode == FS_X_EXCHANGE_OPEN;
         for (int f = 0; f < nf; f++)
-            relax(mode, g, in[f], rhs ? rhs[f] : nullptr, stale ? stale[f] : nullptr, out[f], flags, a, c, b[f], in_zero, false);
-        if (fuse_halo) halo_n(g, out, nf);
+            relax(mode, g, in[f], rhs ? rhs[f] : nullptr, stale ? stale[f] : nullptr, out[f], flags, a, c, b[f], in_zero,
+                  exch ? FS_X_NONE : xmode);
+        if (exch) halo_n(g, out, nf);
     }
     void halo_n(const FsGrid &g, float *const *fields, int nf) {
         for (int f = 0; f < nf; f++) halo(g, fields[f]);
@@ -284,17 +301,18 @@ struct HostExec {
         uint32_t magic;
         int32_t rank, nzl, kb, ke, zoff, nbuf;
         void *raw_field[11];
-        std::atomic<unsigned> *seq;
+        std::atomic<unsigned> *seq, *ack;
     };
     struct Peer {
         bool present = false;
         float *base[11] = {};
-        std::atomic<unsigned> *seq = nullptr;
+        std::atomic<unsigned> *seq = nullptr, *ack = nullptr;
         int nzl = 0, zoff = 0;
     };
     bool halo_on = false;
     Peer lo, hi;
-    std::atomic<unsigned> *my_seq = nullptr;
+    std::atomic<unsigned> *my_seq = nullptr, *my_ack = nullptr;
+    bool ack_since_last_op = false;
     unsigned ops = 0;
     std::vector<float *> bufs;
     int buf_index(const float *p) const {
@@ -305,11 +323,22 @@ struct HostExec {
     static void spin(std::atomic<unsigned> *a, unsigned target) {
         while ((int)(a->load(std::memory_order_acquire) - target) < 0) std::this_thread::yield();
     }
+    // after an extended sweep: the ghost planes the neighbours' last operation filled have been read
+    void ack() {
+        if (!halo_on) return;
+        my_ack->store(ops, std::memory_order_release);
+        ack_since_last_op = true;
+    }
     void halo(const FsGrid &g, float *field) {
         if (!halo_on) return;
         const unsigned op = ++ops;
         if (lo.present) spin(lo.seq, op - 1);
         if (hi.present) spin(hi.seq, op - 1);
+        if (ack_since_last_op) { // the neighbours ran the same extended sweep: wait until they have read their ghosts
+            if (lo.present) spin(lo.ack, op - 1);
+            if (hi.present) spin(hi.ack, op - 1);
+            ack_since_last_op = false;
+        }
         const int bi = field ? buf_index(field) : -1;
         if (bi >= 0) {
             if (lo.present) memcpy(lo.base[bi] + g.sz * (lo.nzl - FS_GHOST), field + g.sz * g.kb, sizeof(float) * g.sz * FS_GHOST);
@@ -324,12 +353,14 @@ struct HostExec {
     void halo_commit() {}
     template <class Core> int halo_export(Core &c, void *blob) {
         if (!my_seq) my_seq = new std::atomic<unsigned>(0);
+        if (!my_ack) my_ack = new std::atomic<unsigned>(0);
         bufs = c.allocated;
         HostBlob b{};
         b.magic = 0x48454d31u; b.rank = c.prm.slab_rank; b.nzl = c.g.nzl; b.kb = c.g.kb; b.ke = c.g.ke; b.zoff = c.g.zoff;
         b.nbuf = (int)bufs.size();
         for (size_t i = 0; i < bufs.size(); i++) b.raw_field[i] = bufs[i];
         b.seq = my_seq;
+        b.ack = my_ack;
         static_assert(sizeof(HostBlob) <= FS_IPC_BLOB_BYTES, "blob too large");
         memcpy(blob, &b, sizeof(b));
         return FS_OK;
@@ -339,7 +370,7 @@ struct HostExec {
         memcpy(&b, blob, sizeof(b));
         if (b.magic != 0x48454d31u || b.rank != expect_rank) { msg = "blob mismatch"; return FS_ERR_BAD_ARGUMENT; }
         for (int i = 0; i < b.nbuf; i++) p.base[i] = (float *)b.raw_field[i];
-        p.seq = b.seq; p.nzl = b.nzl; p.zoff = b.zoff; p.present = true;
+        p.seq = b.seq; p.ack = b.ack; p.nzl = b.nzl; p.zoff = b.zoff; p.present = true;
         return FS_OK;
     }
     template <class Core> int halo_connect(Core &c, const void *lower_blob, const void *upper_blob, int same_process) {
