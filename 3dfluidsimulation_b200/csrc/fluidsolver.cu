@@ -135,6 +135,8 @@ struct CudaExec {
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
         if (const char *e = getenv("FS_EXTEND")) extend_sweeps = e[0] != '0';
+        if (const char *e = getenv("FS_XCHG_IN_SWEEP")) xchg_in_sweep = e[0] != '0';
+        if (const char *e = getenv("FS_PUSH_CTAS")) push_ctas = atoi(e);
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
         if (const char *e = getenv("FS_NO_PAIR")) { if (e[0] == '1') pair_mode = 0; }
         if (const char *e = getenv("FS_PAIR_SLABS")) pair_slabs = e[0] != '0';
@@ -326,9 +328,13 @@ struct CudaExec {
             const dim3 block(bx, by, 1);
             cudaStream_t ls = st;                                  // stream of the next launch
             int kl_b = kl0, kl_e = kl0 + cnt, kl_alt = 0, zc = 1;  // plane range / chunk length of the next launch
+            FsSweepXchg xc{};
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
     do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
-         launch_on(ls, relax_vec4<MODE_, HZ_>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, kl_alt); } while (0)
+         launch_on(ls, relax_vec4<MODE_, HZ_, false>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, kl_alt, xc); } while (0)
+#define FS_LAUNCH_RELAX_XCHG(MODE_, NZ_) \
+    do { const dim3 grid(gxn, gyn, (NZ_) * nf + 1); \
+         launch_on(ls, relax_vec4<MODE_, true, true>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, 0, 1, l2_ahead, kl_alt, xc); } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \
          else { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_JACOBI, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_JACOBI, false, NZ_, BASE_, STRIDE_); } } while (0)
@@ -348,7 +354,25 @@ struct CudaExec {
                 FS_LAUNCH_RELAX_MODE((mid + zc - 1) / zc, 0, 1);
             };
             const int be = 4, ee = 3; // planes per end of an exchange sweep's / an extended sweep's boundary launch (see below)
-            if (exchange && cnt >= 2 * be + 4) {
+            if (exchange && xchg_in_sweep && g.hz && cnt >= 2 * be + 4) {
+                // ONE launch: ends, push CTAs, middle (relax_vec4<.., XCHG = true>)
+                if (fork_open) join_fork();
+                const unsigned op = ++ops_since_commit;
+                xc.h = halo_args(g, out, nf, op);
+                xc.h.need_ack = ack_since_last_op ? 1 : 0;
+                ack_since_last_op = false;
+                xc.plane_elems = g.sz * FS_GHOST;
+                xc.ends = be;
+                xc.ends_ctas = (unsigned)(2 * nf * gxn * gyn);
+                int pc = push_ctas > 0 ? push_ctas : 16 * nf;
+                if (pc > gxn * gyn) pc = gxn * gyn;
+                xc.push_ctas = (unsigned)pc;
+                const int mid = cnt - 2 * be;
+                kl_b = kl0; kl_e = kl0 + cnt; kl_alt = kl0 + cnt - be; zc = chunk_for(mid);
+                const int nz = 2 + (mid + zc - 1) / zc;
+                if (mode == FS_MODE_SMOOTH) FS_LAUNCH_RELAX_XCHG(FS_MODE_SMOOTH, nz);
+                else FS_LAUNCH_RELAX_XCHG(FS_MODE_JACOBI, nz);
+            } else if (exchange && cnt >= 2 * be + 4) {
                 // fork: side stream = the two ends of the slab, then the P2P push kernel (stores them into the neighbours'
                 // ghosts, signals, awaits theirs); main stream = everything between, concurrently; join
                 if (fork_open) join_fork();                        // (callers pair OPEN with EXTEND; defensive)
@@ -383,6 +407,7 @@ struct CudaExec {
                 if (extend) halo_ack_on_stream(st);
             }
 #undef FS_LAUNCH_RELAX_MODE
+#undef FS_LAUNCH_RELAX_XCHG
 #undef FS_LAUNCH_RELAX
             return;
         }
@@ -400,6 +425,8 @@ struct CudaExec {
         if (extend) halo_ack_on_stream(st);
     }
     bool extend_sweeps = true;    // FS_EXTEND=0: every sweep exchanges (one halo operation per sweep)
+    bool xchg_in_sweep = true;    // FS_XCHG_IN_SWEEP=0: fork / join with a separate push kernel instead of the single launch
+    int push_ctas = 0;            // FS_PUSH_CTAS: CTAs of the single launch that carry the halo operation (default 16 per field)
     bool fork_open = false;       // an FS_X_EXCHANGE_OPEN sweep has left the side stream un-joined
     void join_fork() {
         FS_CUDA(cudaEventRecord(ev_join, st_halo));

@@ -142,7 +142,7 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
 // one exchange hides behind two interior launches.  (Fusing wait / store / signal INTO relax_vec4 was built twice --
 // round 1 inlined, round 2 as a separate instantiation for the ends -- and measured slower both times: register
 // pressure in the 64-register sweep, profiles/r01d_halo_variants.md, profiles/r02e_exchange.md.)
-enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_ERROR = 5, FS_HF_ACK_FROM_LO = 6, FS_HF_ACK_FROM_HI = 7, FS_HF_WORDS = 8 };
+enum { FS_HF_FROM_LO = 0, FS_HF_FROM_HI = 1, FS_HF_BASE = 2, FS_HF_CNT_LO = 3, FS_HF_ENDS = 4, FS_HF_ERROR = 5, FS_HF_ACK_FROM_LO = 6, FS_HF_ACK_FROM_HI = 7, FS_HF_WORDS = 8 };
 
 #define FS_BATCH 3 // fields per batched launch / halo operation (the velocity components)
 struct FsHaloArgs {
@@ -194,45 +194,51 @@ __device__ __forceinline__ unsigned halo_seq(const FsHaloArgs &h) {
     return *(volatile const unsigned *)(h.my_flags + FS_HF_BASE) + h.op_offset;
 }
 
-// Copies the FS_GHOST boundary planes of up to FS_BATCH fields into the neighbours' ghost planes (nf = 0: pure fence)
-// after waiting for seq-1, then signals seq and waits for the neighbours' seq.  plane_elems = FS_GHOST*nx*ny.
-__global__ void __launch_bounds__(256)
-halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
+// One CTA's share of halo operation h: copies the FS_GHOST boundary planes of up to FS_BATCH fields into the neighbours'
+// ghost planes (nf = 0: pure fence) after waiting for seq-1, then signals seq and (last CTA to finish) waits for the
+// neighbours' seq.  plane_elems = FS_GHOST*nx*ny.  cta / ncta: this CTA's index among the CTAs working on the operation;
+// tid / nthr: linear thread index / CTA size.  ends_target > 0: the planes are being produced by other CTAs of the SAME
+// launch (relax_vec4<.., XCHG>), which count themselves in FS_HF_ENDS when their stores are done -- wait for that many.
+__device__ __forceinline__ void halo_push_cta(const FsHaloArgs &h, const long long plane_elems, const unsigned cta, const unsigned ncta,
+                                           const unsigned tid, const unsigned nthr, const unsigned ends_target) {
     __shared__ unsigned s_seq;
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const unsigned seq = halo_seq(h);
-        unsigned long long *tr = (h.trace && blockIdx.x == 0) ? h.trace + 4ull * (seq % h.trace_cap) : nullptr;
-        if (tr) tr[0] = fs_globaltimer_ns();             // kernel start
+        unsigned long long *tr = (h.trace && cta == 0) ? h.trace + 4ull * (seq % h.trace_cap) : nullptr;
+        if (tr) tr[0] = fs_globaltimer_ns();             // start
         if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
         if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
         if (h.need_ack) { // ... and they have finished reading the ghost planes that operation filled (extended sweeps)
             if (h.lo_flags) halo_spin_until(h.my_flags + FS_HF_ACK_FROM_LO, seq - 1, h.my_flags + FS_HF_ERROR);
             if (h.hi_flags) halo_spin_until(h.my_flags + FS_HF_ACK_FROM_HI, seq - 1, h.my_flags + FS_HF_ERROR);
         }
-        if (tr) tr[1] = fs_globaltimer_ns();             // neighbours' previous operation seen
+        if (ends_target) halo_spin_until(h.my_flags + FS_HF_ENDS, ends_target, h.my_flags + FS_HF_ERROR);
+        if (tr) tr[1] = fs_globaltimer_ns();             // neighbours' previous operation seen (and my planes complete)
         s_seq = seq;
     }
     __syncthreads();
-    const long long n4 = plane_elems / 4, stride = (long long)gridDim.x * blockDim.x;
+    const long long n4 = plane_elems / 4, stride = (long long)ncta * nthr;
 #pragma unroll
     for (int f = 0; f < FS_BATCH; f++) {
         if (f >= h.nf) break;
         float *lo_dst = h.lo_plane[f], *hi_dst = h.hi_plane[f];
         const float *lo_src = h.lo_src[f], *hi_src = h.hi_src[f];
-        for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
-            if (lo_dst) reinterpret_cast<float4 *>(lo_dst)[t] = reinterpret_cast<const float4 *>(lo_src)[t];
-            if (hi_dst) reinterpret_cast<float4 *>(hi_dst)[t] = reinterpret_cast<const float4 *>(hi_src)[t];
+        // (ld.cg: the planes may have been written by other SMs during this very launch)
+        for (long long t = (long long)cta * nthr + tid; t < n4; t += stride) {
+            if (lo_dst) reinterpret_cast<float4 *>(lo_dst)[t] = __ldcg(reinterpret_cast<const float4 *>(lo_src) + t);
+            if (hi_dst) reinterpret_cast<float4 *>(hi_dst)[t] = __ldcg(reinterpret_cast<const float4 *>(hi_src) + t);
         }
-        for (long long t = n4 * 4 + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < plane_elems; t += stride) {
-            if (lo_dst) lo_dst[t] = lo_src[t];
-            if (hi_dst) hi_dst[t] = hi_src[t];
+        for (long long t = n4 * 4 + (long long)cta * nthr + tid; t < plane_elems; t += stride) {
+            if (lo_dst) lo_dst[t] = __ldcg(lo_src + t);
+            if (hi_dst) hi_dst[t] = __ldcg(hi_src + t);
         }
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         __threadfence_system();
-        if (atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == gridDim.x - 1) {
+        if (atomicAdd(h.my_flags + FS_HF_CNT_LO, 1u) == ncta - 1) {
             h.my_flags[FS_HF_CNT_LO] = 0;
+            if (ends_target) h.my_flags[FS_HF_ENDS] = 0;  // every CTA of the operation has seen the count: re-arm it
             __threadfence_system();
             unsigned long long *tr = h.trace ? h.trace + 4ull * (s_seq % h.trace_cap) : nullptr;
             if (tr) tr[2] = fs_globaltimer_ns();         // all planes stored
@@ -245,6 +251,10 @@ halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
             if (tr) tr[3] = fs_globaltimer_ns();         // neighbours' planes of this operation have landed
         }
     }
+}
+__global__ void __launch_bounds__(256)
+halo_push_kernel(const FsHaloArgs h, long long plane_elems) {
+    halo_push_cta(h, plane_elems, blockIdx.x, gridDim.x, threadIdx.x, blockDim.x, 0u);
 }
 
 __global__ void halo_commit_kernel(unsigned *flags, unsigned ops) { flags[FS_HF_BASE] += ops; }
@@ -334,13 +344,41 @@ tilemap_scan_kernel(int *cum, int ntiles, int nzl) {
         cum[(long long)kl * ntiles + t] = count;
     }
 }
-template <int MODE, bool HZ>
+// XCHG = true: the sweep of a z-slab that also carries its halo operation, as ONE launch.  Block order (blockIdx.z is the
+// slowest index, CTAs are dispatched in linear order): first the two ENDS of the slab (x.ends planes each, every field),
+// then one z-slice whose first x.push_ctas CTAs are not sweep CTAs at all but run halo_push_cta -- they wait until the ends
+// CTAs have counted themselves done (FS_HF_ENDS), store the boundary planes into the neighbours' ghost planes, signal, and
+// the last of them waits for the neighbours' planes -- then the MIDDLE chunks, which hide all of that.  Because the push
+// CTAs are dispatched BEFORE the middle CTAs they hold their SM slots from the start; a separate push kernel only gets
+// slots when the middle launch (64 registers x 1024 threads = the whole register file of every SM) has no CTA left to
+// dispatch, which serialised the exchange behind the sweep (profiles/r02e_exchange.md).  The hot loop is untouched: the
+// ends CTAs add one atomic after it, the push CTAs leave before it.
+struct FsSweepXchg {
+    FsHaloArgs h;
+    long long plane_elems;   // FS_GHOST * nx * ny
+    int ends;                // planes per end
+    unsigned push_ctas;      // CTAs of the push slice that work on the operation
+    unsigned ends_ctas;      // CTAs of the two ends (all fields): the count that completes FS_HF_ENDS
+};
+template <int MODE, bool HZ, bool XCHG>
 __global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
            const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
-           const int zc_stride, const int l2_ahead, const int kl_alt) {
-    const int fld = batch.nf > 1 ? (int)(blockIdx.z % (unsigned)batch.nf) : 0;
-    const int zblk = batch.nf > 1 ? (int)(blockIdx.z / (unsigned)batch.nf) : (int)blockIdx.z;
+           const int zc_stride, const int l2_ahead, const int kl_alt, const FsSweepXchg x) {
+    unsigned bz = blockIdx.z;
+    if (XCHG) {
+        const unsigned push_slice = 2u * (unsigned)batch.nf;
+        if (bz == push_slice) {
+            const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
+            if (cta < x.push_ctas)
+                halo_push_cta(x.h, x.plane_elems, cta, x.push_ctas, threadIdx.y * blockDim.x + threadIdx.x,
+                              blockDim.x * blockDim.y, x.ends_ctas);
+            return;
+        }
+        if (bz > push_slice) bz -= 1;
+    }
+    const int fld = batch.nf > 1 ? (int)(bz % (unsigned)batch.nf) : 0;
+    const int zblk = batch.nf > 1 ? (int)(bz / (unsigned)batch.nf) : (int)bz;
     const float *__restrict__ in = fld == 0 ? batch.in[0] : (fld == 1 ? batch.in[1] : batch.in[2]);
     const float *__restrict__ rhs = fld == 0 ? batch.rhs[0] : (fld == 1 ? batch.rhs[1] : batch.rhs[2]);
     const float *stale = fld == 0 ? batch.stale[0] : (fld == 1 ? batch.stale[1] : batch.stale[2]);
@@ -355,8 +393,12 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     // between them, so the exchange overlaps the interior (fluidsolver.cu, CudaExec::relax).
     // (zc_stride == 0: a two-chunk launch for the two ends of a slab -- chunk 0 starts at kl_begin, chunk 1 at kl_alt)
     const int zc = zc_base + zblk * zc_stride;
-    const int k_lo = zc_stride == 0 ? (zblk == 0 ? kl_begin : kl_alt) : kl_begin + zc * zchunk;
-    const int k_hi = min(k_lo + zchunk, kl_end);
+    int k_lo = zc_stride == 0 ? (zblk == 0 ? kl_begin : kl_alt) : kl_begin + zc * zchunk;
+    int k_hi = min(k_lo + zchunk, kl_end);
+    if (XCHG) { // ends: [kl_begin, +ends) and [kl_alt = kl_end - ends, kl_end); middle chunks between
+        k_lo = zblk == 0 ? kl_begin : (zblk == 1 ? kl_alt : kl_begin + x.ends + (zblk - 2) * zchunk);
+        k_hi = zblk < 2 ? k_lo + x.ends : min(k_lo + zchunk, kl_alt);
+    }
     const bool active = x0 < g.nx && j <= g.ny - 2 && k_lo < k_hi;
     if (active) {
     const FsDivisor dv = fs_make_divisor(c);
@@ -474,6 +516,13 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
         cur = next;
     }
     } // active
+    if (XCHG && zblk < 2) { // an ends CTA: its planes are complete
+        __syncthreads();
+        if (threadIdx.x == 0 && threadIdx.y == 0) {
+            __threadfence();
+            atomicAdd(x.h.my_flags + FS_HF_ENDS, 1u);
+        }
+    }
 }
 
 // ---- float4 versions of the once-per-step stencils --------------------------------------------------------
