@@ -175,12 +175,13 @@ __device__ __forceinline__ unsigned long long fs_globaltimer_ns() {
 }
 // Bounded: a neighbour that died or never launched must not leave this GPU spinning for ever.  After
 // FS_HALO_TIMEOUT_NS the waiter records FS_HF_ERROR = 2 in its own flag block and carries on (the fields are then
-// wrong; fs_sync / fs_get_* report the error).
+// wrong; fs_sync / fs_get_* report the error); later waits of the same slab give up at once.
 #ifndef FS_HALO_TIMEOUT_NS
 #define FS_HALO_TIMEOUT_NS 30000000000ull
 #endif
 __device__ __forceinline__ void halo_spin_until(const unsigned *flag, unsigned target, unsigned *err_word) {
     if ((int)(ld_acquire_sys(flag) - target) >= 0) return;
+    if (*(volatile unsigned *)err_word == 2u) return; // an earlier wait has already timed out: do not add 30 s per wait
     const unsigned long long t0 = fs_globaltimer_ns();
     while ((int)(ld_acquire_sys(flag) - target) < 0) {
         __nanosleep(64);
