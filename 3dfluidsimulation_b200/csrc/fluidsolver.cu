@@ -83,25 +83,14 @@ struct CudaExec {
     // changed the back-to-back sweeps, 60.6 -> 52.5 us at N = 8, and left the graph-replayed step where it was); the
     // attribute is captured with the node.
     int halo_priority = 0;
-    bool halo_prio_attr = false; // FS_HALO_PRIORITY=1: highest stream priority + launch attribute for the side stream
-    // Programmatic dependent launch of the relaxation sweeps (FS_PDL=0 disables): relax_vec4 releases its dependents at its
-    // first instruction and waits for its predecessor (griddepcontrol.wait) only before its first load of field data, so the
-    // next sweep's CTAs are resident, with their index arithmetic done, the moment the previous sweep retires.  A sweep is
-    // 8 us (128^3) to 45 us (a 64-plane slab) of work against ~10 us of launch latency + ramp per dependent launch.
-    bool pdl = true, pdl_next = false;
+    bool halo_prio_attr = true; // FS_HALO_NO_PRIORITY=1 switches both the stream priority and the attribute off
     template <class... KArgs, class... Args>
     void launch_on(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args &&...args) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = stream;
-        cudaLaunchAttribute attr[2];
+        cudaLaunchAttribute attr[1];
         int n = 0;
-        if (stream == st_halo && halo_prio_attr) { attr[n].id = cudaLaunchAttributePriority; attr[n].val.priority = halo_priority; n++; }
-        if (pdl_next) { // programmatic dependent launch: this kernel's CTAs may become resident while its predecessor drains
-            attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            attr[n].val.programmaticStreamSerializationAllowed = 1;
-            n++;
-            pdl_next = false;
-        }
+        if (stream == st_halo && halo_prio_attr) { attr[0].id = cudaLaunchAttributePriority; attr[0].val.priority = halo_priority; n = 1; }
         cfg.attrs = attr; cfg.numAttrs = n;
         FS_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
         launches++;
@@ -146,7 +135,6 @@ struct CudaExec {
         if (const char *e = getenv("FS_NO_ADVECT_VEC4")) no_advect_vec4 = e[0] == '1';
         if (const char *e = getenv("FS_NO_TILEMAP")) no_tilemap = e[0] == '1';
         if (const char *e = getenv("FS_EXTEND")) extend_sweeps = e[0] != '0';
-        if (const char *e = getenv("FS_PDL")) pdl = e[0] != '0';
         if (const char *e = getenv("FS_XCHG_IN_SWEEP")) xchg_in_sweep = e[0] != '0';
         if (const char *e = getenv("FS_PUSH_CTAS")) push_ctas = atoi(e);
         if (const char *e = getenv("FS_PAIR")) pair_mode = atoi(e);
@@ -342,10 +330,10 @@ struct CudaExec {
             int kl_b = kl0, kl_e = kl0 + cnt, kl_alt = 0, zc = 1;  // plane range / chunk length of the next launch
             FsSweepXchg xc{};
 #define FS_LAUNCH_RELAX(MODE_, HZ_, NZ_, BASE_, STRIDE_) \
-    do { const dim3 grid(gxn, gyn, (NZ_) * nf); pdl_next = pdl && ls == st; \
+    do { const dim3 grid(gxn, gyn, (NZ_) * nf); \
          launch_on(ls, relax_vec4<MODE_, HZ_, false>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, BASE_, STRIDE_, l2_ahead, kl_alt, xc); } while (0)
 #define FS_LAUNCH_RELAX_XCHG(MODE_, NZ_) \
-    do { const dim3 grid(gxn, gyn, (NZ_) * nf + 1); pdl_next = pdl && ls == st; \
+    do { const dim3 grid(gxn, gyn, (NZ_) * nf + 1); \
          launch_on(ls, relax_vec4<MODE_, true, true>, grid, block, g, batch, flags, tiles, a, c, iz, kl_b, kl_e, zc, 0, 1, l2_ahead, kl_alt, xc); } while (0)
 #define FS_LAUNCH_RELAX_MODE(NZ_, BASE_, STRIDE_) \
     do { if (mode == FS_MODE_SMOOTH) { if (g.hz) FS_LAUNCH_RELAX(FS_MODE_SMOOTH, true, NZ_, BASE_, STRIDE_); else FS_LAUNCH_RELAX(FS_MODE_SMOOTH, false, NZ_, BASE_, STRIDE_); } \

@@ -107,13 +107,6 @@ division_selftest_kernel(float c, unsigned long long first, unsigned long long c
     if (bad) atomicAdd(mismatches, bad);
 }
 
-// ---- programmatic dependent launch (sm_90+) ----------------------------------------------------------------
-// release: dependents launched with cudaLaunchAttributeProgrammaticStreamSerialization may start once every CTA of this
-// grid has executed this (or exited).  wait: returns when the grid this one depends on has completed and its memory is
-// visible.  Both are no-ops in a launch without the attribute.
-__device__ __forceinline__ void fs_pdl_release() { asm volatile("griddepcontrol.launch_dependents;"); }
-__device__ __forceinline__ void fs_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-
 // ---- z-slab halo exchange over peer memory (NVLink P2P) ----------------------------------------------
 // One process (or handle) per GPU.  A slab's neighbours map its field buffers and its flag block (CUDA IPC
 // or plain peer access) and STORE boundary planes straight into its ghost planes; there is no receive
@@ -373,15 +366,11 @@ __global__ void __launch_bounds__(256, 4)
 relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__ flags, const FsTileMap tiles, const float a,
            const float c, const int in_zero, const int kl_begin, const int kl_end, const int zchunk, const int zc_base,
            const int zc_stride, const int l2_ahead, const int kl_alt, const FsSweepXchg x) {
-    // programmatic dependent launch (no-ops when launched without the attribute): let the next kernel's CTAs become resident
-    // as soon as every CTA of this one has started; this kernel in turn touches no field data before fs_pdl_wait()
-    fs_pdl_release();
     unsigned bz = blockIdx.z;
     if (XCHG) {
         const unsigned push_slice = 2u * (unsigned)batch.nf;
         if (bz == push_slice) {
             const unsigned cta = blockIdx.y * gridDim.x + blockIdx.x;
-            fs_pdl_wait();
             if (cta < x.push_ctas)
                 halo_push_cta(x.h, x.plane_elems, cta, x.push_ctas, threadIdx.y * blockDim.x + threadIdx.x,
                               blockDim.x * blockDim.y, x.ends_ctas);
@@ -435,7 +424,6 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     float *pout = out + idx0;
     const long long sy = g.sy, sz = g.sz;
     float4 prev = make_float4(0.f, 0.f, 0.f, 0.f), cur = prev, next = prev;
-    fs_pdl_wait(); // everything above read launch parameters and the (static) tile map only
     if (!in_zero) {
         cur = ld4(pin);
         if (HZ) prev = ld4(pin - sz);
@@ -532,7 +520,6 @@ relax_vec4(const FsGrid g, const FsRelaxBatch batch, const uint8_t *__restrict__
     if (XCHG && zblk < 2) { // an ends CTA: its planes are complete
         __syncthreads();
         if (threadIdx.x == 0 && threadIdx.y == 0) {
-            fs_pdl_wait(); // (immediate if this thread was active; the counter belongs to this launch only after the previous one)
             __threadfence();
             atomicAdd(x.h.my_flags + FS_HF_ENDS, 1u);
         }
