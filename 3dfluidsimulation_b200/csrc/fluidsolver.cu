@@ -83,7 +83,7 @@ struct CudaExec {
     // changed the back-to-back sweeps, 60.6 -> 52.5 us at N = 8, and left the graph-replayed step where it was); the
     // attribute is captured with the node.
     int halo_priority = 0;
-    bool halo_prio_attr = true; // FS_HALO_NO_PRIORITY=1 switches both the stream priority and the attribute off
+    bool halo_prio_attr = false; // FS_HALO_PRIORITY=1: highest stream priority + launch-priority attribute for the side stream
     template <class... KArgs, class... Args>
     void launch_on(cudaStream_t stream, void (*kernel)(KArgs...), dim3 grid, dim3 block, Args &&...args) {
         cudaLaunchConfig_t cfg{};
