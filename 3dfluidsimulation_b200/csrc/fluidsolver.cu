@@ -424,7 +424,10 @@ struct CudaExec {
         if (exchange) halo_n_on_stream(g, out, nf, st); // per-cell fallback: push after the whole sweep
         if (extend) halo_ack_on_stream(st);
     }
-    bool extend_sweeps = true;    // FS_EXTEND=0: every sweep exchanges (one halo operation per sweep)
+    // FS_EXTEND=1: two sweeps per halo operation (extended sweeps).  Built and bit exact; measured neutral on NVSwitch
+    // (N = 8, 512^3: 18.0 vs 17.7 ms per step) because the single-launch exchange sweep already hides the operation, so the
+    // default is one operation per sweep and no acknowledgement launches.  For links slower than NVLink.
+    bool extend_sweeps = false;
     bool xchg_in_sweep = true;    // FS_XCHG_IN_SWEEP=0: fork / join with a separate push kernel instead of the single launch
     int push_ctas = 0;            // FS_PUSH_CTAS: CTAs of the single launch that carry the halo operation (default 16 per field)
     bool fork_open = false;       // an FS_X_EXCHANGE_OPEN sweep has left the side stream un-joined

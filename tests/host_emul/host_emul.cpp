@@ -59,8 +59,8 @@ struct HostExec {
     // xmode: FS_X_* (fs_cellops.cuh).  An extended sweep also computes the first ghost plane on each side that has a
     // neighbour, from local data only, and acknowledges the ghost planes it read (see halo()).
     bool can_extend(const FsGrid &g) const {
-        const char *e = getenv("FS_EXTEND");
-        return halo_on && g.hz && !(e && e[0] == '0');
+        const char *e = getenv("FS_EXTEND"); // opt-in, as in the CUDA executor
+        return halo_on && g.hz && e && e[0] == '1';
     }
     void relax(int mode, const FsGrid &g, const float *in, const float *rhs, const float *stale, float *out,
                const uint8_t *flags, float a, float c, int b, bool in_zero, int xmode) {

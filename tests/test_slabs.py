@@ -60,6 +60,17 @@ def test_emulated_slabs_match_single_grid(emul_lib, oracle, count, obstacles):
     run_group_vs_oracle(emul_lib, oracle, 12, 10, 16, count, obstacles, vscale=1.5)
 
 
+@pytest.mark.parametrize("count", [2, 3, 4])
+@pytest.mark.parametrize("obstacles", [False, True])
+@pytest.mark.parametrize("kd,kp", [(4, 6), (5, 7), (1, 2)])
+def test_emulated_slabs_extended_sweeps(emul_lib, oracle, count, obstacles, kd, kp, monkeypatch):
+    """FS_EXTEND=1: two sweeps per halo operation -- the first of each couple also computes the first ghost plane from the
+    two-deep ghost zone and exchanges nothing, the second exchanges; readers of ghost planes outside an operation
+    acknowledge.  Even and odd iteration counts; still the single-grid oracle bit for bit."""
+    monkeypatch.setenv("FS_EXTEND", "1")
+    run_group_vs_oracle(emul_lib, oracle, 12, 10, 16, count, obstacles, vscale=1.5, kd=kd, kp=kp)
+
+
 @pytest.mark.parametrize("count", [2, 3])
 @pytest.mark.parametrize("kp", [5, 6])
 def test_emulated_slabs_red_black(emul_lib, oracle, count, kp):
@@ -148,6 +159,14 @@ def _gpu_count():
     import torch
 
     return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("obstacles", [False, True])
+def test_two_gpu_slabs_extended_sweeps(cuda_lib, oracle, obstacles, monkeypatch):
+    """FS_EXTEND=1 on two real GPUs (the executor reads the variable when the handle is created)."""
+    monkeypatch.setenv("FS_EXTEND", "1")
+    test_two_gpu_slabs_in_process(cuda_lib, oracle, obstacles, True)
 
 
 @pytest.mark.gpu
