@@ -57,3 +57,19 @@ def test_workloads_follow_baseline_json():
     assert bench.WORKLOADS["512"][:3] == (512, 20, 80)
     assert "Gvoxel" in bench.METRIC and "voxel" in json.dumps(base).lower()
     assert bench.step_bytes_per_voxel(20, 80) == 88 * 20 + 26 * 80 + 182
+
+
+def test_reference_arm_line_on_cpu():
+    """`bench.py --impl reference` needs no GPU: it times the CPU oracle and prints one JSON line whose grid is the
+    sample that actually ran (the driver computes the ratio from it)."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "32",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300, check=True).stdout
+    line = json.loads(out.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["config"]["grid"] == [32, 32, 32] and line["config"]["workload_grid"] == [32, 32, 32]
+    assert line["cpu_baseline"]["kind"] == "port-tidy" and line["cpu_baseline"]["faithful"]["kind"] == "port-faithful"
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["unit"] == "Gvoxel-updates/s" and line["metric"] == importlib.import_module("bench").METRIC
