@@ -297,9 +297,11 @@ def timed_run(job, s, one_step, steps, warmup, sample_clocks=False, settle_s=0.5
         times.append(time.perf_counter() - t0)
     per_step = max(min(times), 1e-4) if times else settle_s  # (the first step also captures the graph: take the fastest)
     extra = int(job.max_over_ranks(float(max(0, int(np.ceil(settle_s / per_step)) - warmup))))
-    for _ in range(min(extra, 200)):
+    extra = min(extra, 200)
+    for _ in range(extra):
         one_step()
     s.sync()
+    timed_run.warmup_steps_run = warmup + extra
     sampler = ClockSampler(job.local) if sample_clocks else None
     job.barrier()
     if sampler:
@@ -429,6 +431,7 @@ def main():
 
     # ---- device-resident throughput ----------------------------------------------------------------------
     ms, launches, clocks = timed_run(job, s, one_step, args.steps, warmup, sample_clocks=True)
+    warmup_steps_run = timed_run.warmup_steps_run
     value = voxels * args.steps / (ms * 1e-3) / 1e9
 
     # ---- end to end through the C ABI with host buffers ---------------------------------------------------
@@ -550,7 +553,7 @@ def main():
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": cfg, "grid": list(dims), "iters_diffuse": kd, "iters_pressure": kp,
                    "solver": "red-black" if kind else "jacobi", "dt": dt, "obstacle": "sphere r=0.1N" if obstacle else "none",
-                   "parallelism": f"z-slabs x{world}", "cuda_graph": graph,
+                   "parallelism": f"z-slabs x{world}", "cuda_graph": graph, "warmup_steps_run": warmup_steps_run,
                    "l2": "state (45 B/voxel) is larger than L2; no flush needed"},
         "roofline": roofline,
         "e2e": {"value": e2e_value, "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": int(h2d_bytes),
