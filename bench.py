@@ -22,10 +22,12 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
                 z-slab of the SAME nx x ny grid (same rows, same coefficients) with 256^3 voxels' worth of planes;
                 "port-tidy" = oracle/fluid_oracle.c, "port-faithful" = oracle/ref_faithful3d.c (static-64 job
                 batches, serial BoundaryJob scans, per-call allocate-and-copy, as FluidSim.cs executes).
-  e2e           same metric through the C ABI with HOST buffers: per step the source cells go host->device and
-                density + pressure (what UpdateVisualization reads, FluidSim.cs:761-768) come back into pinned host
-                memory; frame_value = the drop-in's frame instead (sources, fs_step, fs_render_rgba of the mid
-                plane + fs_get_metrics: 4 MB instead of 1 GB of readback).
+  e2e           same metric through the C ABI with HOST buffers, wall clock.  value = the drop-in's frame (Update(),
+                FluidSim.cs:390-450): source cells host->device, fs_step, fs_render_rgba of the viewed plane and
+                fs_get_metrics device->host, a host sync every step (use the on-device consumers
+                in the e2e loop).  full_fields_value = round 1's definition, kept beside it: density + pressure of the
+                whole grid (what UpdateVisualization reads in the 2D reference, :761-768; 1 GB at 512^3) come back into
+                pinned host memory every step through the pipelined readback.
   parity_check  (N > 1) before timing, a small slab case over the same N ranks is compared bit for bit with a
                 1-GPU handle on rank 0.
   extra         short 1024^3 K_p = 100 runs (BASELINE configs[4]: Jacobi and red-black, strong scaling) and the
@@ -467,6 +469,7 @@ def main():
         s.metrics()
     s.sync()
     frame_s = job.max_over_ranks(time.perf_counter() - t0)
+    frame_value = voxels * args.steps / frame_s / 1e9
     del host
 
     # ---- roofline of the step's kernels, live, CUDA events on the solver stream --------------------------------
@@ -556,13 +559,17 @@ def main():
                    "parallelism": f"z-slabs x{world}", "cuda_graph": graph, "warmup_steps_run": warmup_steps_run,
                    "l2": "state (45 B/voxel) is larger than L2; no flush needed"},
         "roofline": roofline,
-        "e2e": {"value": e2e_value, "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": e2e_s / args.steps * 1e3,
-                "frame_value": voxels * args.steps / frame_s / 1e9,
-                "frame_d2h_bytes_per_step": int(rgba.nbytes + 12),
-                "note": "per step: fs_add_source_cells (host->device) + fs_step + fs_get_field_async(density, pressure) into "
-                        "pinned host memory, fs_wait_transfers before the clock stops; frame_value = sources + fs_step + "
-                        "fs_render_rgba(mid plane) + fs_get_metrics, the drop-in's Update()"},
+        "e2e": {"value": frame_value, "unit": "Gvoxel-updates/s", "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(rgba.nbytes + 12), "ms_per_step": frame_s / args.steps * 1e3,
+                "frame_value": frame_value,
+                "full_fields_value": e2e_value, "full_fields_d2h_bytes_per_step": d2h_bytes,
+                "full_fields_ms_per_step": e2e_s / args.steps * 1e3,
+                "note": "value = the drop-in's Update() through the C ABI, wall clock, a host sync every step: "
+                        "fs_add_source_cells (host->device through pinned staging) + fs_step + fs_render_rgba (the viewed "
+                        "plane, device->host) + fs_get_metrics (device->host) -- what FluidSim.cs:390-450 does per frame; "
+                        "full_fields_value = the same with density + pressure of the WHOLE grid read back every step "
+                        "(fs_get_field_async into pinned host memory, fs_wait_transfers before the clock stops): this was "
+                        "`value` in round 1 and is PCIe / host-ingest bound at 8 GPUs (1 GB per step)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -73,3 +73,39 @@ def test_reference_arm_line_on_cpu():
     assert line["cpu_baseline"]["kind"] == "port-tidy" and line["cpu_baseline"]["faithful"]["kind"] == "port-faithful"
     assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
     assert line["unit"] == "Gvoxel-updates/s" and line["metric"] == importlib.import_module("bench").METRIC
+
+
+def test_bench_main_dry_run_on_the_emulated_core(emul_lib, monkeypatch, capsys):
+    """The whole of bench.main() -- timed loop, e2e loops, per-kernel list, roofline, CPU baseline leg, JSON line -- driven
+    on CPU: torch.cuda is stubbed out and the build step hands back the host-emulated core.  Numbers are meaningless here;
+    the point is that the line the driver parses is produced and carries every contract key."""
+    import sys
+
+    import torch
+
+    bench = importlib.import_module("bench")
+    bld = importlib.import_module("3dfluidsimulation_b200.build")
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *_: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *_: None)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, pin_memory=False, **k: real_empty(*a, **k))
+    monkeypatch.setattr(bld, "build", lambda *a, **k: emul_lib)
+    monkeypatch.setattr(bld, "LIB", emul_lib)
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--workload", "32", "--grid", "16,16,16", "--steps", "2", "--warmup", "1",
+                                      "--no-extra", "--no-graph"])
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["steps"] == 2 and line["n_gpus"] == 1 and line["value"] > 0 and line["gpu_launches"] > 0
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernels"):
+        assert key in line["roofline"], key
+    assert {k["kernel"] for k in line["roofline"]["kernels"]} >= {"relax_vec4<JACOBI>", "relax_vec4<SMOOTH>", "divergence_vec4"}
+    e2e = line["e2e"]
+    assert e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] == 16 * 16 * 16 + 12
+    assert e2e["full_fields_value"] > 0 and e2e["full_fields_d2h_bytes_per_step"] == 2 * 16 ** 3 * 4
+    assert line["cpu_baseline"]["kind"] == "port-tidy" and line["config"]["warmup_steps_run"] >= 3
